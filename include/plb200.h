@@ -1,0 +1,208 @@
+/*
+ * plb200.h — C ABI of the B200-native state-vector engine (libplb200.so).
+ *
+ * This is the drop-in boundary for pennylane-lightning's hot path: gate
+ * application on a 2^n complex amplitude vector, the measurement reductions on it, and the
+ * adjoint-Jacobian sweep.  Every entry point is `extern "C"`, takes plain pointers and
+ * sizes only (no C++/torch types) and returns an int status: 0 = ok, non-zero = failure with
+ * the message available from plb200_last_error() (thread-local).  The C++ classes in
+ * pennylane-lightning_b200/host/ (StateVectorB200 / Measurements / AdjointJacobian, the
+ * mirrors of the reference's CRTP interfaces) convert a non-zero status into the reference's
+ * LightningException text, as PL_ABORT does (core/utils/Error.hpp:111-139).
+ *
+ * Conventions shared with the reference:
+ *  - one contiguous array of interleaved (re,im); wire w <-> index bit (n-1-w), wire 0 = MSB
+ *    (GateImplementationsLM.hpp:690-699);
+ *  - gate matrices row-major, wires[0] = most-significant matrix bit (StateVectorBase.hpp:195);
+ *  - params and matrices cross the ABI as double / interleaved complex128 for both
+ *    precisions (the engine narrows to fp32 for a c64 state);
+ *  - all device work is enqueued on the stream given at creation (one stream per state
+ *    vector, as DevTag does in core/utils/cuda_utils/DevTag.hpp); calls that return host
+ *    data synchronise that stream before returning.
+ *
+ * There is NO CPU fallback: every compute entry point fails with a CUDA error when no
+ * sm_100 device is present.
+ */
+#ifndef PLB200_H
+#define PLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plb200_sv plb200_sv;   /* opaque state vector (device resident) */
+typedef struct plb200_obs plb200_obs; /* opaque observable tree (host resident) */
+
+#define PLB200_C64 32  /* complex<float>  */
+#define PLB200_C128 64 /* complex<double> */
+
+/* Flattened tape of operations: the C image of OpsData<StateVectorT>
+ * (core/algorithms/JacobianData.hpp:39-253) and of the argument lists of
+ * StateVectorBase::applyOperations (core/simulators/base/StateVectorBase.hpp:116-160).
+ * Arrays *_off have n_ops+1 entries (CSR style). mats_off counts complex elements. */
+typedef struct plb200_ops_t {
+    int64_t n_ops;
+    const char *const *names;
+    const int64_t *wires;
+    const int64_t *wires_off;
+    const int64_t *ctrl_wires;
+    const int64_t *ctrl_off;
+    const uint8_t *ctrl_values; /* indexed like ctrl_wires */
+    const double *params;
+    const int64_t *params_off;
+    const uint8_t *inverses;
+    const double *mats; /* interleaved complex128, row-major; may be empty per op */
+    const int64_t *mats_off;
+} plb200_ops_t;
+
+/* ------------------------------------------------------------------ errors / info */
+const char *plb200_last_error(void);
+int plb200_device_count(int *count);
+/* major*10+minor of `device`, e.g. 100 for B200 (BindingsCudaUtils.hpp:47-115 get_gpu_arch) */
+int plb200_device_arch(int device, int *arch);
+const char *plb200_version(void);
+
+/* ------------------------------------------------------------------ lifecycle
+ * replaces StateVectorCudaManaged(num_qubits, DevTag) — lightning_gpu/StateVectorCudaManaged.hpp
+ * ctor family / LGPUBindings.hpp:283-287.  `stream` is a cudaStream_t (NULL = legacy default). */
+int plb200_sv_create(plb200_sv **out, int64_t num_qubits, int precision, int device,
+                     void *stream);
+/* wraps device memory owned by the caller (e.g. a torch tensor / an NVLink-peer-mapped slab) */
+int plb200_sv_create_external(plb200_sv **out, int64_t num_qubits, int precision, int device,
+                              void *stream, void *device_ptr);
+int plb200_sv_destroy(plb200_sv *sv);
+int64_t plb200_sv_num_qubits(const plb200_sv *sv);
+int64_t plb200_sv_length(const plb200_sv *sv);
+int plb200_sv_precision(const plb200_sv *sv);
+int plb200_sv_device(const plb200_sv *sv);
+void *plb200_sv_device_ptr(const plb200_sv *sv);
+int plb200_sv_sync(plb200_sv *sv);
+/* number of CUDA kernels this library has launched for `sv` since creation */
+int64_t plb200_sv_kernel_launches(const plb200_sv *sv);
+
+/* ------------------------------------------------------------------ copies
+ * DeviceToHost / HostToDevice / DeviceToDevice / updateData — LGPUBindings.hpp:289-349,
+ * StateVectorCudaBase.hpp CopyHostDataToGpu/CopyGpuDataToHost.  n_elems = complex elements. */
+int plb200_sv_h2d(plb200_sv *sv, const void *host, int64_t n_elems, int async);
+int plb200_sv_d2h(plb200_sv *sv, void *host, int64_t n_elems, int async);
+int plb200_sv_d2d(plb200_sv *dst, const plb200_sv *src);
+
+/* ------------------------------------------------------------------ state preparation
+ * StateVectorLQubit.hpp:881-1036 (resetStateVector, setBasisState, setStateVector, collapse,
+ * normalize) and lightning_gpu/initSV.cu:76-136. */
+int plb200_sv_reset(plb200_sv *sv);
+int plb200_sv_set_basis_state_index(plb200_sv *sv, int64_t index);
+int plb200_sv_set_basis_state(plb200_sv *sv, const int64_t *state, const int64_t *wires,
+                              int64_t n_wires);
+/* values: 2^n_wires interleaved complex128 on host; other wires are put in |0> */
+int plb200_sv_set_state_vector(plb200_sv *sv, const double *values, const int64_t *wires,
+                               int64_t n_wires);
+/* zero the state, then sv[indices[i]] = values[i] (setStateVector(indices, values)) */
+int plb200_sv_set_state_indices(plb200_sv *sv, const int64_t *indices, const double *values,
+                                int64_t n);
+int plb200_sv_collapse(plb200_sv *sv, int64_t wire, int branch);
+int plb200_sv_normalize(plb200_sv *sv);
+
+/* ------------------------------------------------------------------ gates
+ * applyOperation(name, [ctrl_wires, ctrl_values,] wires, inverse, params) —
+ * StateVectorLQubit.hpp:378-430; names from core/gates/Constant.hpp:30-135.
+ * n_ctrl == 0 selects the uncontrolled overload. */
+int plb200_sv_apply(plb200_sv *sv, const char *name, const int64_t *ctrl_wires,
+                    const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires,
+                    int64_t n_wires, int inverse, const double *params, int64_t n_params);
+/* applyMatrix / applyControlledMatrix — StateVectorLQubit.hpp:571-710 */
+int plb200_sv_apply_matrix(plb200_sv *sv, const double *matrix, const int64_t *ctrl_wires,
+                           const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires,
+                           int64_t n_wires, int inverse);
+/* applyPauliRot — GateImplementationsLM.hpp:575-629 */
+int plb200_sv_apply_pauli_rot(plb200_sv *sv, const int64_t *wires, int64_t n_wires, int inverse,
+                              double theta, const char *word);
+/* applyGenerator -> scaling factor — GateImplementationsLM.hpp:2181-2952 */
+int plb200_sv_apply_generator(plb200_sv *sv, const char *name, const int64_t *ctrl_wires,
+                              const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires,
+                              int64_t n_wires, int adj, double *scale);
+/* applyOperations over a whole tape; `fuse` != 0 lets the engine schedule the tape into
+ * cache-blocked passes (same arithmetic per gate, fewer HBM sweeps). */
+int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse);
+/* statistics of the last plb200_sv_apply_ops call: [0]=gates, [1]=HBM passes (kernel launches) */
+int plb200_sv_last_apply_stats(const plb200_sv *sv, int64_t *stats2);
+
+/* ------------------------------------------------------------------ linear algebra
+ * innerProdC / scaleAndAdd / squaredNorm — lightning_qubit/utils/LinearAlgebra.hpp:87-159,322-400;
+ * cuBLAS dotc/axpy/scal wrappers — cuda_utils/LinearAlg.hpp:97-280. */
+int plb200_sv_dot(const plb200_sv *a, const plb200_sv *b, double *out_re_im); /* <a|b> */
+int plb200_sv_axpy(plb200_sv *y, const double *alpha_re_im, const plb200_sv *x);
+int plb200_sv_scale(plb200_sv *sv, const double *alpha_re_im);
+int plb200_sv_norm2(const plb200_sv *sv, double *out);
+
+/* ------------------------------------------------------------------ observables
+ * NamedObs / HermitianObs / TensorProdObs / Hamiltonian — core/observables/Observables.hpp:128-584,
+ * lightning_qubit/observables/ObservablesLQubit.hpp:48-370.  Children are copied. */
+int plb200_obs_named(plb200_obs **out, const char *name, const int64_t *wires, int64_t n_wires,
+                     const double *params, int64_t n_params);
+int plb200_obs_hermitian(plb200_obs **out, const double *matrix, const int64_t *wires,
+                         int64_t n_wires);
+int plb200_obs_tensor(plb200_obs **out, const plb200_obs *const *terms, int64_t n_terms);
+int plb200_obs_hamiltonian(plb200_obs **out, const double *coeffs,
+                           const plb200_obs *const *terms, int64_t n_terms);
+int plb200_obs_destroy(plb200_obs *obs);
+/* Observable::applyInPlace(sv) — Observables.hpp:63 */
+int plb200_obs_apply(const plb200_obs *obs, plb200_sv *sv);
+
+/* ------------------------------------------------------------------ measurements
+ * MeasurementsLQubit.hpp:90-163 (probs), :213-305 (expval matrix / named), :372-394 (expval obs),
+ * :431-508 (var), :646-679 (generate_samples); MeasurementsGPU.hpp:449-530 (Pauli words). */
+/* n_wires < 0 => all wires in order; out has 2^n_wires doubles (host) */
+int plb200_probs(plb200_sv *sv, const int64_t *wires, int64_t n_wires, double *out);
+int plb200_expval_named(plb200_sv *sv, const char *name, const int64_t *wires, int64_t n_wires,
+                        double *out);
+int plb200_var_named(plb200_sv *sv, const char *name, const int64_t *wires, int64_t n_wires,
+                     double *out);
+int plb200_expval_matrix(plb200_sv *sv, const double *matrix, const int64_t *wires,
+                         int64_t n_wires, double *out);
+int plb200_var_matrix(plb200_sv *sv, const double *matrix, const int64_t *wires,
+                      int64_t n_wires, double *out);
+/* sum_k coeffs[k] <word_k>: words[k] is a string over {I,X,Y,Z}; its wires are
+ * wires[wires_off[k] .. wires_off[k+1]).  All words are evaluated in one fused launch. */
+int plb200_expval_pauli_words(plb200_sv *sv, const char *const *words, const int64_t *wires,
+                              const int64_t *wires_off, const double *coeffs, int64_t n_words,
+                              double *out);
+/* the same, returning every <word_k> separately in out[n_words] */
+int plb200_expval_pauli_words_each(plb200_sv *sv, const char *const *words,
+                                   const int64_t *wires, const int64_t *wires_off,
+                                   int64_t n_words, double *out);
+int plb200_expval_obs(plb200_sv *sv, const plb200_obs *obs, double *out);
+int plb200_var_obs(plb200_sv *sv, const plb200_obs *obs, double *out);
+/* alias-method sampling with std::mt19937(seed) exactly as MeasurementKernels.hpp:308-381;
+ * seed < 0 => std::random_device.  out: shots x n_wires uint64 (wire order as given);
+ * n_wires < 0 => all wires. */
+int plb200_generate_samples(plb200_sv *sv, const int64_t *wires, int64_t n_wires, int64_t shots,
+                            int64_t seed, uint64_t *out);
+
+/* ------------------------------------------------------------------ adjoint Jacobian
+ * AdjointJacobian::adjointJacobian — AdjointJacobianLQubit.hpp:347-491.  jac has
+ * n_obs*n_tp doubles, observable-major (the layout returned to Python, Bindings.hpp:710-729).
+ * `sv` is not modified. apply_ops != 0 applies the tape to a copy of sv first. */
+int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, int64_t n_obs,
+                            const plb200_ops_t *ops, const int64_t *trainable, int64_t n_tp,
+                            int apply_ops, double *jac);
+
+/* ------------------------------------------------------------------ distributed support
+ * Local half of a global<->local index-bit swap (replaces custatevecSVSwapWorker /
+ * StateVectorKokkosMPI::swapGlobalLocalWires, StateVectorKokkosMPI.hpp:747-889).
+ * pack:   buf[j] = sv[insert(j, bit, 1-keep)]  for the 2^(n-1) amplitudes whose local index bit
+ *         `bit` differs from `keep`;  unpack writes them back.  buf is device memory. */
+int plb200_sv_pack_bit(const plb200_sv *sv, int64_t bit, int keep, void *buf);
+int plb200_sv_unpack_bit(plb200_sv *sv, int64_t bit, int keep, const void *buf);
+/* in-place exchange of the half with local bit `bit` != keep against a peer-mapped slab
+ * (cudaDeviceEnablePeerAccess over NVLink); each GPU of the pair calls it with its own keep. */
+int plb200_sv_swap_bit_peer(plb200_sv *sv, int64_t bit, int keep, void *peer_device_ptr,
+                            int do_half);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLB200_H */

@@ -1,0 +1,695 @@
+// Reductions and state utilities of the plb200 engine (sm_100a): norm / dot / axpy, probs,
+// Pauli-word inner products (expval + adjoint generator overlaps in ONE pass, many words per
+// launch), small-matrix expval, Pauli-sum (Hamiltonian) application, state preparation helpers
+// and the local half of the distributed index-bit swap.
+// All sums accumulate in fp64 per thread, reduce by warp shuffle, then by a fixed-order second
+// stage -> deterministic for a given launch shape.
+#include "device.cuh"
+
+#include <algorithm>
+
+namespace plb200 {
+
+double *StateVec::reduce_buf(size_t n_doubles) {
+    if (n_doubles > red_cap) {
+        set_device();
+        if (red) PLB_CUDA(cudaFree(red));
+        red_cap = std::max<size_t>(n_doubles, 1 << 16);
+        PLB_CUDA(cudaMalloc(&red, red_cap * sizeof(double)));
+    }
+    return red;
+}
+void *StateVec::table_buf(size_t bytes) {
+    if (bytes > tbl_cap) {
+        set_device();
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        if (tbl) PLB_CUDA(cudaFree(tbl));
+        tbl_cap = std::max<size_t>(bytes, 1 << 16);
+        PLB_CUDA(cudaMalloc(&tbl, tbl_cap));
+    }
+    return tbl;
+}
+
+namespace {
+constexpr int kThreads = 256;
+
+template <int NV> __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *out) {
+    __shared__ double sm[NV][kThreads / 32];
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < NV; q++) sm[q][warp] = v[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double s = 0;
+            for (int w = 0; w < kThreads / 32; w++) s += sm[q][w];
+            out[q] = s;
+        }
+    }
+}
+
+// partials laid out [row][nparts][NV]; out[row][NV]
+template <int NV> __global__ void final_reduce_kernel(const double *partials, int nparts, double *out) {
+    const int row = blockIdx.x;
+    double v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) v[q] = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+#pragma unroll
+        for (int q = 0; q < NV; q++) v[q] += partials[(static_cast<size_t>(row) * nparts + i) * NV + q];
+    block_reduce_store<NV>(v, out + static_cast<size_t>(row) * NV);
+}
+
+inline int reduce_blocks(const StateVec &sv, uint64_t items) {
+    uint64_t b = (items + kThreads * 4 - 1) / (kThreads * 4);
+    return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(b, uint64_t(sv.sm_count) * 16)));
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads) norm2_kernel(const T2 *__restrict__ a, uint64_t len, double *partials) {
+    double v[1] = {0};
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const T2 x = a[i];
+        v[0] += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+    }
+    block_reduce_store<1>(v, partials + blockIdx.x);
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    dot_kernel(const T2 *__restrict__ a, const T2 *__restrict__ b, uint64_t len, double *partials) {
+    double v[2] = {0, 0};
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const T2 x = a[i], y = b[i];
+        v[0] += static_cast<double>(x.x) * y.x + static_cast<double>(x.y) * y.y;
+        v[1] += static_cast<double>(x.x) * y.y - static_cast<double>(x.y) * y.x;
+    }
+    block_reduce_store<2>(v, partials + 2 * blockIdx.x);
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads) scale_kernel(T2 *__restrict__ a, uint64_t len, T2 alpha) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
+        a[i] = cmul(a[i], alpha);
+}
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    axpy_kernel(T2 *__restrict__ y, const T2 *__restrict__ x, uint64_t len, T2 alpha) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
+        y[i] = cfma(alpha, x[i], y[i]);
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads) probs_all_kernel(const T2 *__restrict__ a, uint64_t len, double *out) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const T2 x = a[i];
+        // re*re + im*im without FMA contraction, as std::norm on the host
+        if constexpr (sizeof(T2) == 16) out[i] = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));
+        else out[i] = static_cast<double>(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+    }
+}
+
+struct ProbsArgs {
+    int k;
+    int bits[40]; // output bit j (lsb-first) <- state bit bits[j]
+};
+// small k: shared-memory histogram per block, merged with fp64 atomics
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    probs_hist_kernel(const T2 *__restrict__ a, uint64_t len, double *out, const __grid_constant__ ProbsArgs p) {
+    extern __shared__ double hist[];
+    const int nout = 1 << p.k;
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const T2 x = a[i];
+        unsigned o = 0;
+        for (int j = 0; j < p.k; j++) o |= static_cast<unsigned>((i >> p.bits[j]) & 1) << j;
+        atomicAdd(&hist[o], static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nout; i += blockDim.x)
+        if (hist[i] != 0.0) atomicAdd(&out[i], hist[i]);
+}
+// large k: one thread per output, ordered sum over the remaining bits
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    probs_gather_kernel(const T2 *__restrict__ a, uint64_t nout, uint64_t nrest, double *out,
+                        const __grid_constant__ ProbsArgs p, const __grid_constant__ BitInsert rest_ins) {
+    const uint64_t o = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (o >= nout) return;
+    uint64_t base = 0;
+    for (int j = 0; j < p.k; j++) base |= ((o >> j) & 1) << p.bits[j];
+    double s = 0;
+    for (uint64_t r = 0; r < nrest; r++) {
+        // rest_ins inserts zeros at the *measured* bit positions
+        const T2 x = a[insert_bits(r, rest_ins) | base];
+        s += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+    }
+    out[o] = s;
+}
+
+// ------------------------------------------------------------------ Pauli-word inner products
+struct WordDev {
+    uint64_t x, z, cmask, cval;
+    int ny;
+    int pad;
+};
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    pauli_inner_kernel(const T2 *__restrict__ a, const T2 *__restrict__ b, uint64_t len,
+                       const WordDev *__restrict__ words, double *partials) {
+    const WordDev w = words[blockIdx.x];
+    double v[2] = {0, 0};
+    const uint64_t stride = static_cast<uint64_t>(gridDim.y) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.y) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        if ((i & w.cmask) != w.cval) continue;
+        const uint64_t j = i ^ w.x;
+        const T2 x = a[i], y = b[j];
+        // conj(x) * y
+        double re = static_cast<double>(x.x) * y.x + static_cast<double>(x.y) * y.y;
+        double im = static_cast<double>(x.x) * y.y - static_cast<double>(x.y) * y.x;
+        if (__popcll(j & w.z) & 1) re = -re, im = -im;
+        v[0] += re;
+        v[1] += im;
+    }
+    // multiply by i^ny once per thread
+    double re = v[0], im = v[1];
+    switch (w.ny & 3) {
+    case 1:
+        v[0] = -im, v[1] = re;
+        break;
+    case 2:
+        v[0] = -re, v[1] = -im;
+        break;
+    case 3:
+        v[0] = im, v[1] = -re;
+        break;
+    default:
+        break;
+    }
+    block_reduce_store<2>(v, partials + 2 * (static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y));
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    pauli_sum_apply_kernel(T2 *__restrict__ out, const T2 *__restrict__ in, uint64_t len,
+                           const WordDev *__restrict__ words, const double *__restrict__ coeffs, int nwords) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        double re = 0, im = 0;
+        for (int k = 0; k < nwords; k++) {
+            const WordDev w = words[k];
+            const uint64_t j = i ^ w.x;
+            const T2 y = in[j];
+            double c = coeffs[k];
+            if (__popcll(j & w.z) & 1) c = -c;
+            double yr = y.x, yi = y.y;
+            switch (w.ny & 3) { // times i^ny
+            case 1: {
+                const double t = yr;
+                yr = -yi, yi = t;
+            } break;
+            case 2:
+                yr = -yr, yi = -yi;
+                break;
+            case 3: {
+                const double t = yr;
+                yr = yi, yi = -t;
+            } break;
+            default:
+                break;
+            }
+            re = fma(c, yr, re);
+            im = fma(c, yi, im);
+        }
+        out[i] = mk<T2>(re, im);
+    }
+}
+
+// --------------------------------------------------------------- <psi|M|psi>, M on k<=4 wires
+template <typename T2> struct MatExpArgs {
+    BitInsert ins;
+    uint64_t ngroups;
+    uint64_t off[16];
+    double2 m[256];
+};
+template <typename T2, int K>
+__global__ void __launch_bounds__(128)
+    expval_matrix_kernel(const T2 *__restrict__ sv, const MatExpArgs<T2> *__restrict__ pp, double *partials) {
+    constexpr int D = 1 << K;
+    __shared__ double2 sm[D * D];
+    const MatExpArgs<T2> &p = *pp;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) sm[i] = p.m[i];
+    __syncthreads();
+    double acc = 0;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+        const uint64_t base = insert_bits(g, p.ins);
+        double2 v[D];
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            const T2 t = sv[base + p.off[c]];
+            v[c] = make_double2(t.x, t.y);
+        }
+#pragma unroll
+        for (int r = 0; r < D; r++) {
+            double2 s = make_double2(0, 0);
+#pragma unroll
+            for (int c = 0; c < D; c++) s = cfma(sm[r * D + c], v[c], s);
+            acc += v[r].x * s.x + v[r].y * s.y; // Re(conj(v_r) s)
+        }
+    }
+    // block reduce (128 threads)
+    __shared__ double red[4];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+}
+
+// ------------------------------------------------------------------------- state helpers
+template <typename T2>
+__global__ void scatter_kernel(T2 *sv, const int64_t *idx, const double2 *vals, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) sv[idx[i]] = mk<T2>(vals[i].x, vals[i].y);
+}
+struct WiresArgs {
+    int k;
+    int tbits[40];
+};
+template <typename T2>
+__global__ void set_on_wires_kernel(T2 *sv, const double2 *vals, uint64_t nvals, const __grid_constant__ WiresArgs p) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nvals) return;
+    uint64_t o = 0;
+    for (int j = 0; j < p.k; j++) o |= ((i >> j) & 1) << p.tbits[j];
+    sv[o] = mk<T2>(vals[i].x, vals[i].y);
+}
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    collapse_kernel(T2 *__restrict__ sv, uint64_t half, const __grid_constant__ BitInsert ins, uint64_t zero_bit) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < half; g += stride)
+        sv[insert_bits(g, ins) | zero_bit] = mk<T2>(0.0, 0.0);
+}
+template <typename T2, bool PACK>
+__global__ void __launch_bounds__(kThreads)
+    pack_kernel(T2 *__restrict__ sv, T2 *__restrict__ buf, uint64_t half, const __grid_constant__ BitInsert ins,
+                uint64_t sel_bit) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < half; g += stride) {
+        const uint64_t i = insert_bits(g, ins) | sel_bit;
+        if constexpr (PACK) buf[g] = sv[i];
+        else sv[i] = buf[g];
+    }
+}
+// In-place exchange with a peer slab over NVLink: this GPU owns the pairs g in [lo, hi) and swaps
+// its amplitude (bit != keep) with the peer's amplitude (bit == keep... i.e. peer's own non-kept
+// half), using 128-bit peer loads/stores.
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    swap_peer_kernel(T2 *__restrict__ mine, T2 *__restrict__ peer, uint64_t lo, uint64_t hi,
+                     const __grid_constant__ BitInsert ins, uint64_t my_bit, uint64_t peer_bit) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < hi; g += stride) {
+        const uint64_t b = insert_bits(g, ins);
+        const T2 a = mine[b | my_bit];
+        const T2 c = peer[b | peer_bit];
+        mine[b | my_bit] = c;
+        peer[b | peer_bit] = a;
+    }
+}
+
+BitInsert single_insert(int bit) {
+    BitInsert bi;
+    bi.n = 1;
+    bi.lowmask[0] = (uint64_t{1} << bit) - 1;
+    return bi;
+}
+
+template <int NV> void finish_reduce(StateVec &sv, double *partials, int rows, int nparts, double *host_out) {
+    double *res = partials + static_cast<size_t>(rows) * nparts * NV;
+    final_reduce_kernel<NV><<<rows, kThreads, 0, sv.stream>>>(partials, nparts, res);
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+    PLB_CUDA(cudaMemcpyAsync(host_out, res, sizeof(double) * rows * NV, cudaMemcpyDeviceToHost, sv.stream));
+    PLB_CUDA(cudaStreamSynchronize(sv.stream));
+}
+
+} // namespace
+
+#define DISPATCH(sv, call64, call32)                                                                     \
+    do {                                                                                                 \
+        if ((sv).precision == 64) {                                                                      \
+            using T2 = double2;                                                                          \
+            call64;                                                                                      \
+        } else {                                                                                         \
+            using T2 = float2;                                                                           \
+            call32;                                                                                      \
+        }                                                                                                \
+    } while (0)
+
+double norm2(StateVec &sv) {
+    sv.set_device();
+    const int nb = reduce_blocks(sv, sv.length());
+    double *part = sv.reduce_buf(static_cast<size_t>(nb) + 8);
+    DISPATCH(sv, (norm2_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), sv.length(), part)),
+             (norm2_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), sv.length(), part)));
+    sv.launches++;
+    double out;
+    finish_reduce<1>(sv, part, 1, nb, &out);
+    return out;
+}
+
+void dot(const StateVec &a, const StateVec &b, StateVec &owner, double out[2]) {
+    PLB_CHECK(a.n == b.n && a.precision == b.precision, "dot: incompatible state vectors");
+    owner.set_device();
+    const int nb = reduce_blocks(owner, a.length());
+    double *part = owner.reduce_buf(2 * static_cast<size_t>(nb) + 8);
+    DISPATCH(a,
+             (dot_kernel<T2><<<nb, kThreads, 0, owner.stream>>>(static_cast<const T2 *>(a.data),
+                                                                static_cast<const T2 *>(b.data), a.length(), part)),
+             (dot_kernel<T2><<<nb, kThreads, 0, owner.stream>>>(static_cast<const T2 *>(a.data),
+                                                                static_cast<const T2 *>(b.data), a.length(), part)));
+    owner.launches++;
+    finish_reduce<2>(owner, part, 1, nb, out);
+}
+
+void scale(StateVec &sv, cd alpha) {
+    sv.set_device();
+    const int nb = reduce_blocks(sv, sv.length());
+    DISPATCH(sv,
+             (scale_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), sv.length(),
+                                                               mk<T2>(alpha.real(), alpha.imag()))),
+             (scale_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), sv.length(),
+                                                               mk<T2>(alpha.real(), alpha.imag()))));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void axpy(StateVec &y, cd alpha, const StateVec &x) {
+    PLB_CHECK(x.n == y.n && x.precision == y.precision, "axpy: incompatible state vectors");
+    y.set_device();
+    const int nb = reduce_blocks(y, y.length());
+    DISPATCH(y,
+             (axpy_kernel<T2><<<nb, kThreads, 0, y.stream>>>(static_cast<T2 *>(y.data), static_cast<const T2 *>(x.data),
+                                                             y.length(), mk<T2>(alpha.real(), alpha.imag()))),
+             (axpy_kernel<T2><<<nb, kThreads, 0, y.stream>>>(static_cast<T2 *>(y.data), static_cast<const T2 *>(x.data),
+                                                             y.length(), mk<T2>(alpha.real(), alpha.imag()))));
+    y.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void probs_all(StateVec &sv, double *host_out) {
+    sv.set_device();
+    double *dout;
+    PLB_CUDA(cudaMalloc(&dout, sv.length() * sizeof(double)));
+    const int nb = reduce_blocks(sv, sv.length());
+    DISPATCH(sv,
+             (probs_all_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), sv.length(), dout)),
+             (probs_all_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), sv.length(), dout)));
+    sv.launches++;
+    cudaError_t e = cudaMemcpyAsync(host_out, dout, sv.length() * sizeof(double), cudaMemcpyDeviceToHost, sv.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sv.stream);
+    cudaFree(dout);
+    PLB_CUDA(e);
+}
+
+void probs_wires(StateVec &sv, const std::vector<int> &bits_msb_first, double *host_out) {
+    sv.set_device();
+    const int k = static_cast<int>(bits_msb_first.size());
+    PLB_CHECK(k <= 40, "too many wires");
+    ProbsArgs p;
+    p.k = k;
+    uint64_t mmask = 0;
+    for (int j = 0; j < k; j++) {
+        p.bits[j] = bits_msb_first[k - 1 - j];
+        mmask |= uint64_t{1} << p.bits[j];
+    }
+    const uint64_t nout = uint64_t{1} << k;
+    double *dout;
+    PLB_CUDA(cudaMalloc(&dout, nout * sizeof(double)));
+    cudaError_t e = cudaSuccess;
+    if (k <= 11) {
+        e = cudaMemsetAsync(dout, 0, nout * sizeof(double), sv.stream);
+        const int nb = reduce_blocks(sv, sv.length());
+        const size_t smem = nout * sizeof(double);
+        DISPATCH(sv,
+                 (probs_hist_kernel<T2><<<nb, kThreads, smem, sv.stream>>>(static_cast<const T2 *>(sv.data),
+                                                                           sv.length(), dout, p)),
+                 (probs_hist_kernel<T2><<<nb, kThreads, smem, sv.stream>>>(static_cast<const T2 *>(sv.data),
+                                                                           sv.length(), dout, p)));
+    } else {
+        BitInsert ins;
+        ins.n = 0;
+        for (int b = 0; b < 64; b++)
+            if (mmask >> b & 1) ins.lowmask[ins.n++] = (uint64_t{1} << b) - 1;
+        const uint64_t nrest = uint64_t{1} << (sv.n - k);
+        const unsigned nb = static_cast<unsigned>((nout + kThreads - 1) / kThreads);
+        DISPATCH(sv,
+                 (probs_gather_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), nout,
+                                                                          nrest, dout, p, ins)),
+                 (probs_gather_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), nout,
+                                                                          nrest, dout, p, ins)));
+    }
+    sv.launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost, sv.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sv.stream);
+    cudaFree(dout);
+    PLB_CUDA(e);
+}
+
+static std::vector<WordDev> to_dev_words(const PauliWordMask *w, int64_t n) {
+    std::vector<WordDev> h(n);
+    for (int64_t i = 0; i < n; i++) h[i] = {w[i].x, w[i].z, w[i].cmask, w[i].cval, w[i].ny, 0};
+    return h;
+}
+
+void pauli_inner(StateVec &a, const StateVec &b, const PauliWordMask *words, int64_t n_words, double *out) {
+    PLB_CHECK(a.n == b.n && a.precision == b.precision, "pauli_inner: incompatible state vectors");
+    if (n_words == 0) return;
+    a.set_device();
+    const int64_t kMaxBatch = 4096;
+    for (int64_t w0 = 0; w0 < n_words; w0 += kMaxBatch) {
+        const int64_t W = std::min(kMaxBatch, n_words - w0);
+        int nchunks = reduce_blocks(a, a.length());
+        // keep the partial buffer bounded when many words are batched
+        nchunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nchunks, (int64_t{1} << 22) / W)));
+        nchunks = std::min(nchunks, 65535);
+        auto h = to_dev_words(words + w0, W);
+        const size_t wbytes = h.size() * sizeof(WordDev);
+        WordDev *dw = static_cast<WordDev *>(a.table_buf(wbytes));
+        PLB_CUDA(cudaMemcpyAsync(dw, h.data(), wbytes, cudaMemcpyHostToDevice, a.stream));
+        PLB_CUDA(cudaStreamSynchronize(a.stream));
+        double *part = a.reduce_buf(2 * static_cast<size_t>(W) * nchunks + 2 * W + 8);
+        dim3 grid(static_cast<unsigned>(W), static_cast<unsigned>(nchunks));
+        DISPATCH(a,
+                 (pauli_inner_kernel<T2><<<grid, kThreads, 0, a.stream>>>(
+                     static_cast<const T2 *>(a.data), static_cast<const T2 *>(b.data), a.length(), dw, part)),
+                 (pauli_inner_kernel<T2><<<grid, kThreads, 0, a.stream>>>(
+                     static_cast<const T2 *>(a.data), static_cast<const T2 *>(b.data), a.length(), dw, part)));
+        a.launches++;
+        PLB_CUDA(cudaGetLastError());
+        finish_reduce<2>(a, part, static_cast<int>(W), nchunks, out + 2 * w0);
+    }
+}
+
+void pauli_sum_apply(StateVec &out, const StateVec &in, const PauliWordMask *words, const double *coeffs,
+                     int64_t n_words) {
+    PLB_CHECK(out.n == in.n && out.precision == in.precision && out.data != in.data,
+              "pauli_sum_apply: needs distinct compatible state vectors");
+    out.set_device();
+    auto h = to_dev_words(words, n_words);
+    const size_t wbytes = h.size() * sizeof(WordDev);
+    const size_t cbytes = n_words * sizeof(double);
+    unsigned char *buf = static_cast<unsigned char *>(out.table_buf(wbytes + cbytes));
+    PLB_CUDA(cudaMemcpyAsync(buf, h.data(), wbytes, cudaMemcpyHostToDevice, out.stream));
+    PLB_CUDA(cudaMemcpyAsync(buf + wbytes, coeffs, cbytes, cudaMemcpyHostToDevice, out.stream));
+    PLB_CUDA(cudaStreamSynchronize(out.stream));
+    const int nb = reduce_blocks(out, out.length());
+    DISPATCH(out,
+             (pauli_sum_apply_kernel<T2><<<nb, kThreads, 0, out.stream>>>(
+                 static_cast<T2 *>(out.data), static_cast<const T2 *>(in.data), out.length(),
+                 reinterpret_cast<const WordDev *>(buf), reinterpret_cast<const double *>(buf + wbytes),
+                 static_cast<int>(n_words))),
+             (pauli_sum_apply_kernel<T2><<<nb, kThreads, 0, out.stream>>>(
+                 static_cast<T2 *>(out.data), static_cast<const T2 *>(in.data), out.length(),
+                 reinterpret_cast<const WordDev *>(buf), reinterpret_cast<const double *>(buf + wbytes),
+                 static_cast<int>(n_words))));
+    out.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+template <typename T2> static double expval_matrix_typed(StateVec &sv, const std::vector<cd> &matrix, const std::vector<int> &tbits) {
+    const int k = static_cast<int>(tbits.size());
+    const int D = 1 << k;
+    std::vector<MatExpArgs<T2>> hv(1);
+    MatExpArgs<T2> &a = hv[0];
+    uint64_t tmask = 0;
+    for (int b : tbits) tmask |= uint64_t{1} << b;
+    a.ins.n = 0;
+    for (int b = 0; b < 64; b++)
+        if (tmask >> b & 1) a.ins.lowmask[a.ins.n++] = (uint64_t{1} << b) - 1;
+    a.ngroups = uint64_t{1} << (sv.n - k);
+    for (int c = 0; c < D; c++) {
+        uint64_t o = 0;
+        for (int j = 0; j < k; j++)
+            if (c >> j & 1) o |= uint64_t{1} << tbits[j];
+        a.off[c] = o;
+    }
+    for (int i = 0; i < D * D; i++) a.m[i] = make_double2(matrix[i].real(), matrix[i].imag());
+    auto *dargs = static_cast<MatExpArgs<T2> *>(sv.table_buf(sizeof(MatExpArgs<T2>)));
+    PLB_CUDA(cudaMemcpyAsync(dargs, &a, sizeof(a), cudaMemcpyHostToDevice, sv.stream));
+    PLB_CUDA(cudaStreamSynchronize(sv.stream));
+    const int nb = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((a.ngroups + 127) / 128, uint64_t(sv.sm_count) * 16)));
+    double *part = sv.reduce_buf(static_cast<size_t>(nb) + 8);
+    const T2 *d = static_cast<const T2 *>(sv.data);
+    switch (k) {
+    case 1:
+        expval_matrix_kernel<T2, 1><<<nb, 128, 0, sv.stream>>>(d, dargs, part);
+        break;
+    case 2:
+        expval_matrix_kernel<T2, 2><<<nb, 128, 0, sv.stream>>>(d, dargs, part);
+        break;
+    case 3:
+        expval_matrix_kernel<T2, 3><<<nb, 128, 0, sv.stream>>>(d, dargs, part);
+        break;
+    default:
+        expval_matrix_kernel<T2, 4><<<nb, 128, 0, sv.stream>>>(d, dargs, part);
+        break;
+    }
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+    double out;
+    finish_reduce<1>(sv, part, 1, nb, &out);
+    return out;
+}
+
+double expval_matrix_small(StateVec &sv, const std::vector<cd> &matrix, const std::vector<int> &tbits) {
+    PLB_CHECK(tbits.size() >= 1 && tbits.size() <= 4, "expval_matrix_small: 1..4 wires");
+    sv.set_device();
+    return sv.precision == 64 ? expval_matrix_typed<double2>(sv, matrix, tbits)
+                              : expval_matrix_typed<float2>(sv, matrix, tbits);
+}
+
+void scatter_values(StateVec &sv, const int64_t *idx, const double *vals, int64_t n) {
+    sv.set_device();
+    PLB_CUDA(cudaMemsetAsync(sv.data, 0, sv.bytes(), sv.stream));
+    if (n == 0) return;
+    const size_t ib = n * sizeof(int64_t), vb = n * 2 * sizeof(double);
+    unsigned char *buf = static_cast<unsigned char *>(sv.table_buf(ib + vb));
+    PLB_CUDA(cudaMemcpyAsync(buf, vals, vb, cudaMemcpyHostToDevice, sv.stream));
+    PLB_CUDA(cudaMemcpyAsync(buf + vb, idx, ib, cudaMemcpyHostToDevice, sv.stream));
+    PLB_CUDA(cudaStreamSynchronize(sv.stream));
+    const unsigned nb = static_cast<unsigned>((n + kThreads - 1) / kThreads);
+    DISPATCH(sv,
+             (scatter_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data),
+                                                                 reinterpret_cast<const int64_t *>(buf + vb),
+                                                                 reinterpret_cast<const double2 *>(buf), n)),
+             (scatter_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data),
+                                                                 reinterpret_cast<const int64_t *>(buf + vb),
+                                                                 reinterpret_cast<const double2 *>(buf), n)));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void set_state_on_wires(StateVec &sv, const double *vals, const std::vector<int> &tbits) {
+    sv.set_device();
+    WiresArgs p;
+    p.k = static_cast<int>(tbits.size());
+    PLB_CHECK(p.k <= 40, "too many wires");
+    for (int j = 0; j < p.k; j++) p.tbits[j] = tbits[j];
+    const uint64_t nvals = uint64_t{1} << p.k;
+    PLB_CUDA(cudaMemsetAsync(sv.data, 0, sv.bytes(), sv.stream));
+    double2 *dv;
+    PLB_CUDA(cudaMalloc(&dv, nvals * sizeof(double2)));
+    cudaError_t e = cudaMemcpyAsync(dv, vals, nvals * sizeof(double2), cudaMemcpyHostToDevice, sv.stream);
+    const unsigned nb = static_cast<unsigned>((nvals + kThreads - 1) / kThreads);
+    if (e == cudaSuccess) {
+        DISPATCH(sv, (set_on_wires_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), dv, nvals, p)),
+                 (set_on_wires_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), dv, nvals, p)));
+        sv.launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sv.stream);
+    cudaFree(dv);
+    PLB_CUDA(e);
+}
+
+void collapse_zero(StateVec &sv, int bit, int keep_value) {
+    sv.set_device();
+    const uint64_t half = sv.length() >> 1;
+    const int nb = reduce_blocks(sv, half);
+    const BitInsert ins = single_insert(bit);
+    const uint64_t zb = keep_value ? 0 : (uint64_t{1} << bit);
+    DISPATCH(sv, (collapse_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), half, ins, zb)),
+             (collapse_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), half, ins, zb)));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void pack_bit(const StateVec &sv, int bit, int keep, void *buf) {
+    sv.set_device();
+    const uint64_t half = sv.length() >> 1;
+    const int nb = reduce_blocks(sv, half);
+    const BitInsert ins = single_insert(bit);
+    const uint64_t sb = keep ? 0 : (uint64_t{1} << bit);
+    DISPATCH(sv,
+             (pack_kernel<T2, true><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), static_cast<T2 *>(buf),
+                                                                    half, ins, sb)),
+             (pack_kernel<T2, true><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), static_cast<T2 *>(buf),
+                                                                    half, ins, sb)));
+    PLB_CUDA(cudaGetLastError());
+}
+void unpack_bit(StateVec &sv, int bit, int keep, const void *buf) {
+    sv.set_device();
+    const uint64_t half = sv.length() >> 1;
+    const int nb = reduce_blocks(sv, half);
+    const BitInsert ins = single_insert(bit);
+    const uint64_t sb = keep ? 0 : (uint64_t{1} << bit);
+    DISPATCH(sv,
+             (pack_kernel<T2, false><<<nb, kThreads, 0, sv.stream>>>(
+                 static_cast<T2 *>(sv.data), const_cast<T2 *>(static_cast<const T2 *>(buf)), half, ins, sb)),
+             (pack_kernel<T2, false><<<nb, kThreads, 0, sv.stream>>>(
+                 static_cast<T2 *>(sv.data), const_cast<T2 *>(static_cast<const T2 *>(buf)), half, ins, sb)));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void swap_bit_peer(StateVec &sv, int bit, int keep, void *peer, int do_half) {
+    // GPU with keep==0 keeps bit==0 amplitudes and gives away bit==1; its peer (keep==1) gives away
+    // bit==0.  Each side processes one half of the pair range so the link is used in both directions.
+    sv.set_device();
+    const uint64_t half = sv.length() >> 1;
+    const uint64_t lo = do_half == 0 ? 0 : (do_half == 1 ? 0 : half / 2);
+    const uint64_t hi = do_half == 0 ? half : (do_half == 1 ? half / 2 : half);
+    const int nb = reduce_blocks(sv, hi - lo);
+    const BitInsert ins = single_insert(bit);
+    const uint64_t my_bit = keep ? 0 : (uint64_t{1} << bit);
+    const uint64_t peer_bit = keep ? (uint64_t{1} << bit) : 0;
+    DISPATCH(sv,
+             (swap_peer_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), static_cast<T2 *>(peer),
+                                                                   lo, hi, ins, my_bit, peer_bit)),
+             (swap_peer_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), static_cast<T2 *>(peer),
+                                                                   lo, hi, ins, my_bit, peer_bit)));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+} // namespace plb200
