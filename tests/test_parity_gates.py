@@ -139,7 +139,9 @@ def test_controlled_generator(plb, ref, name, dtype):
 def test_pauli_rot(plb, ref, dtype):
     n = 7
     rng = np.random.default_rng(5)
-    words = ["X", "Y", "Z", "XX", "XY", "YZ", "ZZ", "ZIZ", "XYZ", "YYYY", "XIZY", "ZZZZZ", "XYZXYZX", "IYI", "III"]
+    # words without "I": the Python layer strips identities before calling applyPauliRot
+    # (lightning_qubit/_state_vector.py:262-269); the C++ kernel treats any non-Z letter as X/Y.
+    words = ["X", "Y", "Z", "XX", "XY", "YZ", "ZZ", "ZXZ", "XYZ", "YYYY", "XZZY", "ZZZZZ", "XYZXYZX", "ZYZ", "YXY"]
     for i, word in enumerate(words):
         wires = [int(x) for x in rng.permutation(n)[: len(word)]]
         theta = float(rng.uniform(0, 2 * np.pi))
@@ -147,6 +149,23 @@ def test_pauli_rot(plb, ref, dtype):
         a.apply_pauli_rot(wires, bool(i % 2), theta, word)
         b.apply_pauli_rot(wires, bool(i % 2), theta, word)
         _close(a, b, dtype)
+
+
+def test_pauli_rot_identity_letters(plb):
+    """'I' letters act as identity: same result as the stripped word on the remaining wires."""
+    st = random_state(6, np.complex128, 3)
+    for word, wires in (("XIZ", [4, 1, 0]), ("IYI", [2, 5, 3]), ("III", [0, 1, 2]), ("ZIIZ", [5, 0, 1, 2])):
+        a = plb.StateVector(6)
+        a.set_state(st)
+        a.apply_pauli_rot(wires, False, 0.81, word)
+        b = plb.StateVector(6)
+        b.set_state(st)
+        kept = [(c, w) for c, w in zip(word, wires) if c != "I"]
+        if kept:
+            b.apply_pauli_rot([w for _, w in kept], False, 0.81, "".join(c for c, _ in kept))
+        else:
+            b.apply("GlobalPhase", [0], False, [0.81 / 2])
+        np.testing.assert_allclose(a.get_state(), b.get_state(), rtol=0, atol=1e-14)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
