@@ -75,6 +75,8 @@ struct StateVec {
     size_t red_cap = 0;
     void *tbl = nullptr; // device table scratch (diag tables / dense matrices)
     size_t tbl_cap = 0;
+    void *plan = nullptr; // device arena for fused-pass plans
+    size_t plan_cap = 0;
     int64_t launches = 0;
     int64_t last_stats[2] = {0, 0};
     int sm_count = 148;
@@ -85,6 +87,7 @@ struct StateVec {
     void set_device() const { PLB_CUDA(cudaSetDevice(device)); }
     double *reduce_buf(size_t n_doubles);
     void *table_buf(size_t bytes);
+    void *plan_buf(size_t bytes);
     void sync() const { PLB_CUDA(cudaStreamSynchronize(stream)); }
 };
 

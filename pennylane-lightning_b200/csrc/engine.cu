@@ -92,7 +92,8 @@ void free_sv(StateVec &s) {
     if (s.owned && s.data) cudaFree(s.data);
     if (s.red) cudaFree(s.red);
     if (s.tbl) cudaFree(s.tbl);
-    s.data = nullptr, s.red = nullptr, s.tbl = nullptr;
+    if (s.plan) cudaFree(s.plan);
+    s.data = nullptr, s.red = nullptr, s.tbl = nullptr, s.plan = nullptr;
 }
 
 // temporary state sharing device/stream/precision with `like`

@@ -1,5 +1,448 @@
+// Cache-blocked ("tile") execution of a tape of canonical ops — the gate-fusion pass.
+//
+// The reference sweeps the whole 2^n vector once per gate ("one full HBM
+// read+write per gate ... no fusion anywhere").  Here the tape is scheduled into PASSES: a pass
+// owns a set T of M index bits (always including the lowest LOW bits so that every global access
+// is a full 128-byte line) and executes, in program order, every pending op whose non-diagonal
+// target bits lie in T — controls and diagonal factors may sit on any bit, since outside T they
+// are uniform per tile.  One CTA loads a tile of 2^M amplitudes into shared memory, runs the
+// pass's ROUNDS on it and writes it back: ONE HBM read+write for the whole group of gates.
+// Inside the tile a round picks R "register bits": each thread pulls the 2^R amplitudes that
+// differ in those bits into registers, applies all of the round's ops there (2x2 updates on
+// register pairs, phases on single registers), and stores them back.  Per-gate arithmetic is the
+// same 2x2 complex update as the un-fused kernels, so results agree to rounding.
+//
+// Gate commutation used by the scheduler: ops acting on disjoint bit sets commute, nothing else.
 #include "fusion.hpp"
 
+#include <algorithm>
+#include <cstring>
+
 namespace plb200 {
-void run_fused(StateVec &sv, const std::vector<COp> &ops) { launch_ops(sv, ops); }
+
+namespace {
+
+constexpr int kR = 4;       // register bits per round (16 amplitudes per thread)
+constexpr int kMaxRoundOps = 4096;
+
+template <typename T2> struct TileCfg;
+template <> struct TileCfg<double2> {
+    static constexpr int M = 12;  // 2^12 x 16 B = 64 KiB tile
+    static constexpr int LOW = 3; // 8 x 16 B = 128 B contiguous
+};
+template <> struct TileCfg<float2> {
+    static constexpr int M = 13;  // 2^13 x 8 B = 64 KiB tile
+    static constexpr int LOW = 4; // 16 x 8 B = 128 B contiguous
+};
+
+// ------------------------------------------------------------------ device-side plan layout
+template <typename T2> struct TileOp {
+    int kind; // 0 = 2x2 on register bit p ; 1 = phase d[parity]
+    int p;
+    uint32_t cmask_l, cval_l, pmask_l, pad;
+    uint64_t cmask_o, cval_o, pmask_o;
+    T2 m[4];
+};
+struct RoundHdr {
+    int first_op, nops;
+    uint32_t lowmask[kR]; // insertion masks (ascending local positions)
+    uint32_t roff[1 << kR];
+};
+struct PassHdr {
+    int nrounds, nops_total;
+    uint64_t ntiles;
+    BitInsert tile_ins; // zeros at the M tile bits
+    // followed by: uint64 goff[2^(M-LOW)], RoundHdr[nrounds], TileOp[nops_total]
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
+
+template <typename T2, int P>
+__device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t jbase,
+                                           const uint32_t *roff) {
+#pragma unroll
+    for (int q = 0; q < (1 << (kR - 1)); q++) {
+        const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
+        const int u1 = u0 | (1 << P);
+        const uint32_t j = jbase | roff[u0];
+        if ((j & op.cmask_l) == op.cval_l) {
+            const T2 a = v[u0], b = v[u1];
+            v[u0] = cfma(op.m[1], b, cmul(op.m[0], a));
+            v[u1] = cfma(op.m[3], b, cmul(op.m[2], a));
+        }
+    }
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
+    tile_kernel(T2 *__restrict__ sv, const unsigned char *__restrict__ plan) {
+    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
+    constexpr int NT = 1 << (M - kR);
+    constexpr int NV = 1 << kR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T2 *tile = reinterpret_cast<T2 *>(smem_raw);
+    uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(T2) << M));
+
+    const PassHdr *hdr = reinterpret_cast<const PassHdr *>(plan);
+    const uint64_t *goff_g = reinterpret_cast<const uint64_t *>(plan + sizeof(PassHdr));
+    const RoundHdr *rounds = reinterpret_cast<const RoundHdr *>(goff_g + (1 << (M - LOW)));
+    const TileOp<T2> *ops = reinterpret_cast<const TileOp<T2> *>(rounds + hdr->nrounds);
+
+    for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
+    __syncthreads();
+    const uint32_t tid = threadIdx.x;
+    const int nrounds = hdr->nrounds;
+
+    for (uint64_t t = blockIdx.x; t < hdr->ntiles; t += gridDim.x) {
+        const uint64_t base = insert_bits(t, hdr->tile_ins);
+        // ---- load the tile (coalesced 128-byte lines)
+        {
+            T2 v[NV];
+#pragma unroll
+            for (int u = 0; u < NV; u++) {
+                const uint32_t j = tid + u * NT;
+                v[u] = sv[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
+            }
+#pragma unroll
+            for (int u = 0; u < NV; u++) tile[swz(tid + u * NT)] = v[u];
+        }
+        __syncthreads();
+        // ---- rounds
+        for (int r = 0; r < nrounds; r++) {
+            const RoundHdr &rh = rounds[r];
+            uint32_t jbase = tid;
+#pragma unroll
+            for (int i = 0; i < kR; i++) {
+                const uint32_t lm = rh.lowmask[i];
+                jbase = ((jbase & ~lm) << 1) | (jbase & lm);
+            }
+            uint32_t roff[NV];
+#pragma unroll
+            for (int u = 0; u < NV; u++) roff[u] = rh.roff[u];
+            T2 v[NV];
+#pragma unroll
+            for (int u = 0; u < NV; u++) v[u] = tile[swz(jbase | roff[u])];
+            for (int k = 0; k < rh.nops; k++) {
+                const TileOp<T2> &op = ops[rh.first_op + k];
+                if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
+                if (op.kind == 0) {
+                    switch (op.p) {
+                    case 0:
+                        apply_pair<T2, 0>(v, op, jbase, roff);
+                        break;
+                    case 1:
+                        apply_pair<T2, 1>(v, op, jbase, roff);
+                        break;
+                    case 2:
+                        apply_pair<T2, 2>(v, op, jbase, roff);
+                        break;
+                    default:
+                        apply_pair<T2, 3>(v, op, jbase, roff);
+                        break;
+                    }
+                } else {
+                    const uint32_t po = __popcll(base & op.pmask_o) & 1;
+#pragma unroll
+                    for (int u = 0; u < NV; u++) {
+                        const uint32_t j = jbase | roff[u];
+                        if ((j & op.cmask_l) == op.cval_l) {
+                            const uint32_t par = (__popc(j & op.pmask_l) & 1) ^ po;
+                            v[u] = cmul(v[u], par ? op.m[1] : op.m[0]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NV; u++) tile[swz(jbase | roff[u])] = v[u];
+            __syncthreads();
+        }
+        // ---- store the tile
+        {
+            T2 v[NV];
+#pragma unroll
+            for (int u = 0; u < NV; u++) v[u] = tile[swz(tid + u * NT)];
+#pragma unroll
+            for (int u = 0; u < NV; u++) {
+                const uint32_t j = tid + u * NT;
+                sv[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------- host scheduler
+struct FOp {
+    uint64_t nd = 0;  // non-diagonal target bits
+    uint64_t all = 0; // every involved bit
+    bool fusable = false;
+    // parity form of a fusable diagonal
+    uint64_t pmask = 0;
+    cd d[2];
+};
+
+FOp classify(const COp &op) {
+    FOp f;
+    uint64_t t = 0;
+    for (int b : op.tbits) t |= uint64_t{1} << b;
+    f.all = t | op.cmask | (op.parity ? op.pmask : 0);
+    if (op.kind == OP_PROJECT) f.all = ~uint64_t{0};
+    if (op.kind == OP_PAIRS && !op.parity && op.tbits.size() == 1 && op.blocks.size() == 1 && op.blocks[0].a == 0 &&
+        op.blocks[0].b == 1) {
+        f.fusable = true;
+        f.nd = t;
+    } else if (op.kind == OP_DIAG) {
+        if (op.parity) {
+            f.fusable = true, f.pmask = op.pmask, f.d[0] = op.pd[0], f.d[1] = op.pd[1];
+        } else if (op.k() == 0) {
+            f.fusable = true, f.pmask = 0, f.d[0] = f.d[1] = op.diag[0];
+        } else if (op.k() == 1) {
+            f.fusable = true, f.pmask = t, f.d[0] = op.diag[0], f.d[1] = op.diag[1];
+        } else if (op.k() == 2 && op.diag[0] == op.diag[3] && op.diag[1] == op.diag[2]) {
+            f.fusable = true, f.pmask = t, f.d[0] = op.diag[0], f.d[1] = op.diag[1];
+        }
+        if (op.k() == 0 && op.cmask == 0) f.all = 0; // global scalar commutes with everything
+    }
+    if (!f.fusable) f.nd = t;
+    return f;
+}
+
+// ops executable (in order) with non-diagonal bits restricted to S; `pending` lists candidates
+void simulate(const std::vector<FOp> &f, const std::vector<int> &pending, uint64_t S, uint64_t full,
+              std::vector<int> &out) {
+    out.clear();
+    uint64_t blocked = 0;
+    for (int i : pending) {
+        const FOp &o = f[i];
+        if (o.fusable && (o.nd & ~S) == 0 && (o.all & blocked) == 0) out.push_back(i);
+        else {
+            blocked |= o.all;
+            if ((blocked & full) == full) break;
+        }
+    }
+}
+
+// greedy growth of a bit set (capacity cap) maximising the number of executable ops
+uint64_t grow(const std::vector<FOp> &f, const std::vector<int> &pending, uint64_t S, int cap, uint64_t allowed,
+              uint64_t full, std::vector<int> &exec) {
+    std::vector<int> tmp;
+    simulate(f, pending, S, full, exec);
+    while (__builtin_popcountll(S) < cap) {
+        // candidate bits: non-diagonal bits of pending ops not in S
+        uint64_t cand = 0;
+        for (int i : pending) cand |= f[i].nd;
+        cand &= allowed & ~S;
+        if (!cand) break;
+        size_t best = exec.size();
+        int best_bit = -1;
+        for (int b = 0; b < 64; b++) {
+            if (!(cand >> b & 1)) continue;
+            simulate(f, pending, S | (uint64_t{1} << b), full, tmp);
+            if (tmp.size() > best) best = tmp.size(), best_bit = b;
+        }
+        if (best_bit < 0) {
+            // no single bit helps (e.g. the next op needs two new bits): take the first blocked op's bits
+            uint64_t need = 0;
+            uint64_t blocked = 0;
+            for (int i : pending) {
+                const FOp &o = f[i];
+                if (o.fusable && (o.all & blocked) == 0 && (o.nd & ~S) != 0 && (o.nd & ~allowed) == 0 &&
+                    __builtin_popcountll(S | o.nd) <= cap) {
+                    need = o.nd & ~S;
+                    break;
+                }
+                if (!(o.fusable && (o.nd & ~S) == 0 && (o.all & blocked) == 0)) blocked |= o.all;
+            }
+            if (!need) break;
+            S |= need;
+        } else
+            S |= uint64_t{1} << best_bit;
+        simulate(f, pending, S, full, exec);
+    }
+    return S;
+}
+
+struct HostPass {
+    std::vector<int> tbits;                 // sorted ascending, size M
+    std::vector<std::vector<int>> rounds;   // op indices per round
+    std::vector<uint64_t> round_bits;       // register bits (global bit masks) per round
+};
+
+template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
+    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
+    const int n = static_cast<int>(sv.n);
+    if (n < M + 1 || ops.size() < 2) {
+        launch_ops(sv, ops);
+        return;
+    }
+    const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
+    std::vector<FOp> f(ops.size());
+    for (size_t i = 0; i < ops.size(); i++) {
+        f[i] = classify(ops[i]);
+        f[i].all &= full;
+    }
+    std::vector<char> done(ops.size(), 0);
+    size_t first = 0;
+    const size_t window = 512;
+    const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
+
+    struct Step {
+        int op = -1;        // >= 0: standalone op
+        size_t off = 0;     // else: plan offset in the arena
+        unsigned grid = 0;
+    };
+    std::vector<Step> steps;
+    std::vector<unsigned char> arena;
+    std::vector<int> pending, exec;
+
+    auto smem_bytes = (sizeof(T2) << M) + (sizeof(uint64_t) << (M - LOW));
+    static bool attr_set_d = false, attr_set_f = false;
+    bool &attr_set = sizeof(T2) == 16 ? attr_set_d : attr_set_f;
+    if (!attr_set) {
+        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem_bytes)));
+        attr_set = true;
+    }
+
+    while (true) {
+        while (first < ops.size() && done[first]) first++;
+        if (first >= ops.size()) break;
+        pending.clear();
+        for (size_t i = first; i < ops.size() && pending.size() < window; i++)
+            if (!done[i]) pending.push_back(static_cast<int>(i));
+        // ---- choose the tile bits
+        uint64_t T = grow(f, pending, lowbits, M, full, full, exec);
+        if (exec.size() < 2) {
+            // nothing worth a tile pass: run the first pending op on its own
+            Step st;
+            st.op = static_cast<int>(first);
+            steps.push_back(st);
+            done[first] = 1;
+            continue;
+        }
+        // pad T to exactly M bits with the lowest free bits
+        for (int b = 0; b < n && __builtin_popcountll(T) < M; b++) T |= uint64_t{1} << b;
+        simulate(f, pending, T, full, exec);
+        std::vector<int> pass_ops = exec;
+        for (int i : pass_ops) done[i] = 1;
+
+        // ---- rounds
+        HostPass hp;
+        for (int b = 0; b < n; b++)
+            if (T >> b & 1) hp.tbits.push_back(b);
+        std::vector<int> rem = pass_ops, rexec;
+        while (!rem.empty()) {
+            uint64_t seed = f[rem[0]].nd; // guarantees progress
+            uint64_t Rb = grow(f, rem, seed, kR, T, full, rexec);
+            // pad to kR bits with tile bits (prefer high local bits: conflict-free shared accesses)
+            for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < kR; i--) Rb |= uint64_t{1} << hp.tbits[i];
+            simulate(f, rem, Rb, full, rexec);
+            if (rexec.empty()) fail("fusion scheduler made no progress");
+            if (rexec.size() > static_cast<size_t>(kMaxRoundOps)) rexec.resize(kMaxRoundOps);
+            hp.rounds.push_back(rexec);
+            hp.round_bits.push_back(Rb);
+            std::vector<int> next;
+            size_t k = 0;
+            for (int i : rem) {
+                if (k < rexec.size() && rexec[k] == i) k++;
+                else next.push_back(i);
+            }
+            rem.swap(next);
+        }
+
+        // ---- encode the plan
+        const size_t goff_n = size_t{1} << (M - LOW);
+        const size_t bytes = sizeof(PassHdr) + goff_n * sizeof(uint64_t) + hp.rounds.size() * sizeof(RoundHdr) +
+                             pass_ops.size() * sizeof(TileOp<T2>);
+        const size_t off = (arena.size() + 255) & ~size_t{255};
+        arena.resize(off + bytes, 0);
+        PassHdr *hdr = reinterpret_cast<PassHdr *>(arena.data() + off);
+        uint64_t *goff = reinterpret_cast<uint64_t *>(arena.data() + off + sizeof(PassHdr));
+        RoundHdr *rh = reinterpret_cast<RoundHdr *>(goff + goff_n);
+        TileOp<T2> *top = reinterpret_cast<TileOp<T2> *>(rh + hp.rounds.size());
+        hdr->nrounds = static_cast<int>(hp.rounds.size());
+        hdr->nops_total = static_cast<int>(pass_ops.size());
+        hdr->ntiles = uint64_t{1} << (n - M);
+        hdr->tile_ins.n = 0;
+        for (int b : hp.tbits) hdr->tile_ins.lowmask[hdr->tile_ins.n++] = (uint64_t{1} << b) - 1;
+        int local_of[64];
+        for (int i = 0; i < 64; i++) local_of[i] = -1;
+        for (int i = 0; i < M; i++) local_of[hp.tbits[i]] = i;
+        for (size_t j = 0; j < goff_n; j++) {
+            uint64_t o = 0;
+            for (int i = LOW; i < M; i++)
+                if ((j >> (i - LOW)) & 1) o |= uint64_t{1} << hp.tbits[i];
+            goff[j] = o;
+        }
+        auto to_local = [&](uint64_t mask) {
+            uint32_t l = 0;
+            for (int i = 0; i < M; i++)
+                if (mask >> hp.tbits[i] & 1) l |= 1u << i;
+            return l;
+        };
+        int op_cursor = 0;
+        for (size_t r = 0; r < hp.rounds.size(); r++) {
+            std::vector<int> rl; // local positions of the register bits, ascending
+            for (int i = 0; i < M; i++)
+                if (hp.round_bits[r] >> hp.tbits[i] & 1) rl.push_back(i);
+            rh[r].first_op = op_cursor;
+            rh[r].nops = static_cast<int>(hp.rounds[r].size());
+            for (int i = 0; i < kR; i++) rh[r].lowmask[i] = (1u << rl[i]) - 1;
+            for (int u = 0; u < (1 << kR); u++) {
+                uint32_t o = 0;
+                for (int i = 0; i < kR; i++)
+                    if (u >> i & 1) o |= 1u << rl[i];
+                rh[r].roff[u] = o;
+            }
+            for (int idx : hp.rounds[r]) {
+                const COp &op = ops[idx];
+                const FOp &fo = f[idx];
+                TileOp<T2> &t = top[op_cursor++];
+                t.cmask_l = to_local(op.cmask & T), t.cval_l = to_local(op.cval & T);
+                t.cmask_o = op.cmask & ~T, t.cval_o = op.cval & ~T;
+                if (op.kind == OP_PAIRS) {
+                    t.kind = 0;
+                    const int lp = local_of[op.tbits[0]];
+                    t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
+                    for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(op.blocks[0].m[q].real(), op.blocks[0].m[q].imag());
+                } else {
+                    t.kind = 1;
+                    t.pmask_l = to_local(fo.pmask & T);
+                    t.pmask_o = fo.pmask & ~T;
+                    t.m[0] = mk<T2>(fo.d[0].real(), fo.d[0].imag());
+                    t.m[1] = mk<T2>(fo.d[1].real(), fo.d[1].imag());
+                }
+            }
+        }
+        Step st;
+        st.off = off;
+        st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sv.sm_count) * 3 * 64));
+        steps.push_back(st);
+    }
+    // ---- upload every pass plan once, then launch the whole schedule back to back
+    unsigned char *dplan = nullptr;
+    if (!arena.empty()) {
+        dplan = static_cast<unsigned char *>(sv.plan_buf(arena.size()));
+        PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, sv.stream));
+        PLB_CUDA(cudaStreamSynchronize(sv.stream)); // arena is a local
+    }
+    for (const Step &st : steps) {
+        if (st.op >= 0) {
+            launch_op(sv, ops[st.op]);
+            continue;
+        }
+        tile_kernel<T2><<<st.grid, 1 << (M - kR), smem_bytes, sv.stream>>>(static_cast<T2 *>(sv.data), dplan + st.off);
+        PLB_CUDA(cudaGetLastError());
+        sv.launches++;
+    }
+}
+
+} // namespace
+
+void run_fused(StateVec &sv, const std::vector<COp> &ops) {
+    sv.set_device();
+    if (sv.precision == 64) run_fused_typed<double2>(sv, ops);
+    else run_fused_typed<float2>(sv, ops);
+}
+
 } // namespace plb200

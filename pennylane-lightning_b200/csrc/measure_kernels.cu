@@ -30,6 +30,17 @@ void *StateVec::table_buf(size_t bytes) {
     return tbl;
 }
 
+void *StateVec::plan_buf(size_t bytes) {
+    if (bytes > plan_cap) {
+        set_device();
+        PLB_CUDA(cudaStreamSynchronize(stream));
+        if (plan) PLB_CUDA(cudaFree(plan));
+        plan_cap = std::max<size_t>(bytes * 2, 1 << 20);
+        PLB_CUDA(cudaMalloc(&plan, plan_cap));
+    }
+    return plan;
+}
+
 namespace {
 constexpr int kThreads = 256;
 
