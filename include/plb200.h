@@ -127,6 +127,9 @@ int plb200_sv_apply_generator(plb200_sv *sv, const char *name, const int64_t *ct
 /* applyOperations over a whole tape; `fuse` != 0 lets the engine schedule the tape into
  * cache-blocked passes (same arithmetic per gate, fewer HBM sweeps). */
 int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse);
+/* host-only dry run of the fusion scheduler for an n-qubit state (no device needed):
+ * out4 = {tile passes, stand-alone kernels, register rounds, gates executed inside tile passes} */
+int plb200_schedule_stats(int64_t num_qubits, int precision, const plb200_ops_t *ops, int64_t *out4);
 /* statistics of the last plb200_sv_apply_ops call: [0]=gates, [1]=HBM passes (kernel launches) */
 int plb200_sv_last_apply_stats(const plb200_sv *sv, int64_t *stats2);
 

@@ -563,6 +563,16 @@ int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse) {
     s.last_stats[1] = s.launches - before;
     ABI_CATCH
 }
+int plb200_schedule_stats(int64_t n, int precision, const plb200_ops_t *ops, int64_t *out4) {
+    ABI_TRY
+    std::vector<COp> all;
+    for (int64_t i = 0; i < ops->n_ops; i++) {
+        auto l = lower_gate(n, call_from_blob(*ops, i));
+        all.insert(all.end(), std::make_move_iterator(l.begin()), std::make_move_iterator(l.end()));
+    }
+    schedule_stats(static_cast<int>(n), precision, all, out4);
+    ABI_CATCH
+}
 int plb200_sv_last_apply_stats(const plb200_sv *sv, int64_t *stats2) {
     stats2[0] = sv->s.last_stats[0];
     stats2[1] = sv->s.last_stats[1];

@@ -36,19 +36,19 @@ template <> struct TileCfg<float2> {
 };
 
 // ------------------------------------------------------------------ device-side plan layout
-template <typename T2> struct TileOp {
+template <typename T2> struct alignas(16) TileOp {
     int kind; // 0 = 2x2 on register bit p ; 1 = phase d[parity]
     int p;
     uint32_t cmask_l, cval_l, pmask_l, pad;
     uint64_t cmask_o, cval_o, pmask_o;
     T2 m[4];
 };
-struct RoundHdr {
+struct alignas(16) RoundHdr {
     int first_op, nops;
     uint32_t lowmask[kR]; // insertion masks (ascending local positions)
     uint32_t roff[1 << kR];
 };
-struct PassHdr {
+struct alignas(16) PassHdr {
     int nrounds, nops_total;
     uint64_t ntiles;
     BitInsert tile_ins; // zeros at the M tile bits
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
     const uint64_t *goff_g = reinterpret_cast<const uint64_t *>(plan + sizeof(PassHdr));
     const RoundHdr *rounds = reinterpret_cast<const RoundHdr *>(goff_g + (1 << (M - LOW)));
     const TileOp<T2> *ops = reinterpret_cast<const TileOp<T2> *>(rounds + hdr->nrounds);
+    static_assert(sizeof(PassHdr) % 16 == 0 && sizeof(RoundHdr) % 16 == 0 && sizeof(TileOp<T2>) % 16 == 0, "plan alignment");
 
     for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
     __syncthreads();
@@ -201,7 +202,7 @@ FOp classify(const COp &op) {
         } else if (op.k() == 2 && op.diag[0] == op.diag[3] && op.diag[1] == op.diag[2]) {
             f.fusable = true, f.pmask = t, f.d[0] = op.diag[0], f.d[1] = op.diag[1];
         }
-        if (op.k() == 0 && op.cmask == 0) f.all = 0; // global scalar commutes with everything
+        if (!op.parity && op.k() == 0 && op.cmask == 0) f.all = 0; // global scalar commutes with everything
     }
     if (!f.fusable) f.nd = t;
     return f;
@@ -268,11 +269,26 @@ struct HostPass {
     std::vector<uint64_t> round_bits;       // register bits (global bit masks) per round
 };
 
-template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
+struct Step {
+    int op = -1;    // >= 0: standalone op
+    size_t off = 0; // else: plan offset in the arena
+    unsigned grid = 0;
+    int nrounds = 0, nops = 0;
+};
+
+// Pure host: schedule `ops` on an n-qubit state into tile passes / stand-alone ops.
+template <typename T2>
+void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vector<Step> &steps,
+                    std::vector<unsigned char> &arena) {
     constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
-    const int n = static_cast<int>(sv.n);
+    steps.clear();
+    arena.clear();
     if (n < M + 1 || ops.size() < 2) {
-        launch_ops(sv, ops);
+        for (size_t i = 0; i < ops.size(); i++) {
+            Step st;
+            st.op = static_cast<int>(i);
+            steps.push_back(st);
+        }
         return;
     }
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
@@ -286,23 +302,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
     const size_t window = 512;
     const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
 
-    struct Step {
-        int op = -1;        // >= 0: standalone op
-        size_t off = 0;     // else: plan offset in the arena
-        unsigned grid = 0;
-    };
-    std::vector<Step> steps;
-    std::vector<unsigned char> arena;
     std::vector<int> pending, exec;
-
-    auto smem_bytes = (sizeof(T2) << M) + (sizeof(uint64_t) << (M - LOW));
-    static bool attr_set_d = false, attr_set_f = false;
-    bool &attr_set = sizeof(T2) == 16 ? attr_set_d : attr_set_f;
-    if (!attr_set) {
-        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem_bytes)));
-        attr_set = true;
-    }
 
     while (true) {
         while (first < ops.size() && done[first]) first++;
@@ -416,8 +416,24 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         }
         Step st;
         st.off = off;
-        st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sv.sm_count) * 3 * 64));
+        st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
+        st.nrounds = hdr->nrounds, st.nops = hdr->nops_total;
         steps.push_back(st);
+    }
+}
+
+template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
+    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
+    std::vector<Step> steps;
+    std::vector<unsigned char> arena;
+    build_schedule<T2>(static_cast<int>(sv.n), sv.sm_count, ops, steps, arena);
+    auto smem_bytes = (sizeof(T2) << M) + (sizeof(uint64_t) << (M - LOW));
+    static bool attr_set_d = false, attr_set_f = false;
+    bool &attr_set = sizeof(T2) == 16 ? attr_set_d : attr_set_f;
+    if (!attr_set && !arena.empty()) {
+        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem_bytes)));
+        attr_set = true;
     }
     // ---- upload every pass plan once, then launch the whole schedule back to back
     unsigned char *dplan = nullptr;
@@ -438,6 +454,18 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
 }
 
 } // namespace
+
+void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
+    std::vector<Step> steps;
+    std::vector<unsigned char> arena;
+    if (precision == 64) build_schedule<double2>(n, 148, ops, steps, arena);
+    else build_schedule<float2>(n, 148, ops, steps, arena);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (const auto &s : steps) {
+        if (s.op >= 0) out[1]++;
+        else out[0]++, out[2] += s.nrounds, out[3] += s.nops;
+    }
+}
 
 void run_fused(StateVec &sv, const std::vector<COp> &ops) {
     sv.set_device();
