@@ -36,8 +36,20 @@ template <> struct TileCfg<float2> {
 };
 
 // ------------------------------------------------------------------ device-side plan layout
+// op kinds inside a tile pass
+enum : int {
+    TK_GENERAL = 0, // complex 2x2 on register bit p
+    TK_DIAG = 1,    // phase m[parity]
+    TK_SWAP = 2,    // [[0,1],[1,0]] (PauliX / CNOT / Toffoli): pure register exchange, no flops
+    TK_REAL = 3,    // real 2x2 (RY, Hadamard)
+    TK_RXLIKE = 4,  // real diagonal, imaginary off-diagonal (RX)
+    TK_DIAG1 = 5,   // phase on the parity-1 half only (m[0] == 1)
+};
+constexpr int kMaxPassOps = 256;
+constexpr int kMaxPassRounds = 22;
+
 template <typename T2> struct alignas(16) TileOp {
-    int kind; // 0 = 2x2 on register bit p ; 1 = phase d[parity]
+    int kind;
     int p;
     uint32_t cmask_l, cval_l, pmask_l, pad;
     uint64_t cmask_o, cval_o, pmask_o;
@@ -52,30 +64,68 @@ struct alignas(16) PassHdr {
     int nrounds, nops_total;
     uint64_t ntiles;
     BitInsert tile_ins; // zeros at the M tile bits
-    // followed by: uint64 goff[2^(M-LOW)], RoundHdr[nrounds], TileOp[nops_total]
+};
+// The whole pass description travels as a __grid_constant__ kernel parameter (constant bank,
+// uniform loads): nothing about the ops is fetched through the LSU/L1 data path.
+template <typename T2> struct alignas(16) PassParams {
+    PassHdr hdr;
+    RoundHdr rounds[kMaxPassRounds];
+    TileOp<T2> ops[kMaxPassOps];
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
 
-template <typename T2, int P>
+template <typename T2, int P, int KIND>
 __device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t jbase,
                                            const uint32_t *roff) {
+    const T2 m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
+    const uint32_t cm = op.cmask_l, cv = op.cval_l;
 #pragma unroll
     for (int q = 0; q < (1 << (kR - 1)); q++) {
         const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
         const int u1 = u0 | (1 << P);
         const uint32_t j = jbase | roff[u0];
-        if ((j & op.cmask_l) == op.cval_l) {
+        if ((j & cm) == cv) {
             const T2 a = v[u0], b = v[u1];
-            v[u0] = cfma(op.m[1], b, cmul(op.m[0], a));
-            v[u1] = cfma(op.m[3], b, cmul(op.m[2], a));
+            if constexpr (KIND == TK_SWAP) {
+                v[u0] = b, v[u1] = a;
+            } else if constexpr (KIND == TK_REAL) {
+                v[u0].x = fma(m1.x, b.x, m0.x * a.x), v[u0].y = fma(m1.x, b.y, m0.x * a.y);
+                v[u1].x = fma(m3.x, b.x, m2.x * a.x), v[u1].y = fma(m3.x, b.y, m2.x * a.y);
+            } else if constexpr (KIND == TK_RXLIKE) {
+                // (m0.x) a + (i m1.y) b ; (i m2.y) a + (m3.x) b
+                v[u0].x = fma(-m1.y, b.y, m0.x * a.x), v[u0].y = fma(m1.y, b.x, m0.x * a.y);
+                v[u1].x = fma(-m2.y, a.y, m3.x * b.x), v[u1].y = fma(m2.y, a.x, m3.x * b.y);
+            } else {
+                v[u0] = cfma(m1, b, cmul(m0, a));
+                v[u1] = cfma(m3, b, cmul(m2, a));
+            }
         }
+    }
+}
+
+template <typename T2, int KIND>
+__device__ __forceinline__ void apply_pair_p(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t jbase,
+                                             const uint32_t *roff) {
+    switch (op.p) {
+    case 0:
+        apply_pair<T2, 0, KIND>(v, op, jbase, roff);
+        break;
+    case 1:
+        apply_pair<T2, 1, KIND>(v, op, jbase, roff);
+        break;
+    case 2:
+        apply_pair<T2, 2, KIND>(v, op, jbase, roff);
+        break;
+    default:
+        apply_pair<T2, 3, KIND>(v, op, jbase, roff);
+        break;
     }
 }
 
 template <typename T2>
 __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
-    tile_kernel(T2 *__restrict__ sv, const unsigned char *__restrict__ plan) {
+    tile_kernel(T2 *__restrict__ sv, const uint64_t *__restrict__ goff_g, const __grid_constant__ PassParams<T2> pp) {
     constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
     constexpr int NT = 1 << (M - kR);
     constexpr int NV = 1 << kR;
@@ -83,11 +133,10 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
     T2 *tile = reinterpret_cast<T2 *>(smem_raw);
     uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(T2) << M));
 
-    const PassHdr *hdr = reinterpret_cast<const PassHdr *>(plan);
-    const uint64_t *goff_g = reinterpret_cast<const uint64_t *>(plan + sizeof(PassHdr));
-    const RoundHdr *rounds = reinterpret_cast<const RoundHdr *>(goff_g + (1 << (M - LOW)));
-    const TileOp<T2> *ops = reinterpret_cast<const TileOp<T2> *>(rounds + hdr->nrounds);
-    static_assert(sizeof(PassHdr) % 16 == 0 && sizeof(RoundHdr) % 16 == 0 && sizeof(TileOp<T2>) % 16 == 0, "plan alignment");
+    const PassHdr *hdr = &pp.hdr;
+    const RoundHdr *rounds = pp.rounds;
+    const TileOp<T2> *ops = pp.ops;
+    static_assert(sizeof(PassParams<T2>) <= 32764, "kernel parameter space");
 
     for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
     __syncthreads();
@@ -126,31 +175,42 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
             for (int k = 0; k < rh.nops; k++) {
                 const TileOp<T2> &op = ops[rh.first_op + k];
                 if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
-                if (op.kind == 0) {
-                    switch (op.p) {
-                    case 0:
-                        apply_pair<T2, 0>(v, op, jbase, roff);
-                        break;
-                    case 1:
-                        apply_pair<T2, 1>(v, op, jbase, roff);
-                        break;
-                    case 2:
-                        apply_pair<T2, 2>(v, op, jbase, roff);
-                        break;
-                    default:
-                        apply_pair<T2, 3>(v, op, jbase, roff);
-                        break;
-                    }
-                } else {
+                switch (op.kind) {
+                case TK_GENERAL:
+                    apply_pair_p<T2, TK_GENERAL>(v, op, jbase, roff);
+                    break;
+                case TK_SWAP:
+                    apply_pair_p<T2, TK_SWAP>(v, op, jbase, roff);
+                    break;
+                case TK_REAL:
+                    apply_pair_p<T2, TK_REAL>(v, op, jbase, roff);
+                    break;
+                case TK_RXLIKE:
+                    apply_pair_p<T2, TK_RXLIKE>(v, op, jbase, roff);
+                    break;
+                case TK_DIAG1: {
                     const uint32_t po = __popcll(base & op.pmask_o) & 1;
+                    const T2 d1 = op.m[1];
+                    const uint32_t cm = op.cmask_l, cv = op.cval_l, pm = op.pmask_l;
 #pragma unroll
                     for (int u = 0; u < NV; u++) {
                         const uint32_t j = jbase | roff[u];
-                        if ((j & op.cmask_l) == op.cval_l) {
-                            const uint32_t par = (__popc(j & op.pmask_l) & 1) ^ po;
-                            v[u] = cmul(v[u], par ? op.m[1] : op.m[0]);
+                        if ((j & cm) == cv && (((__popc(j & pm) & 1) ^ po) != 0)) v[u] = cmul(v[u], d1);
+                    }
+                } break;
+                default: {
+                    const uint32_t po = __popcll(base & op.pmask_o) & 1;
+                    const T2 d0 = op.m[0], d1 = op.m[1];
+                    const uint32_t cm = op.cmask_l, cv = op.cval_l, pm = op.pmask_l;
+#pragma unroll
+                    for (int u = 0; u < NV; u++) {
+                        const uint32_t j = jbase | roff[u];
+                        if ((j & cm) == cv) {
+                            const uint32_t par = (__popc(j & pm) & 1) ^ po;
+                            v[u] = cmul(v[u], par ? d1 : d0);
                         }
                     }
+                } break;
                 }
             }
 #pragma unroll
@@ -271,7 +331,8 @@ struct HostPass {
 
 struct Step {
     int op = -1;    // >= 0: standalone op
-    size_t off = 0; // else: plan offset in the arena
+    size_t off = 0; // else: offset of the pass's goff table in the arena (bytes)
+    size_t params = 0; // index into the params vector
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
 };
@@ -279,7 +340,8 @@ struct Step {
 // Pure host: schedule `ops` on an n-qubit state into tile passes / stand-alone ops.
 template <typename T2>
 void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vector<Step> &steps,
-                    std::vector<unsigned char> &arena) {
+                    std::vector<unsigned char> &arena, std::vector<PassParams<T2>> &params) {
+    params.clear();
     constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
     steps.clear();
     arena.clear();
@@ -323,8 +385,8 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
         // pad T to exactly M bits with the lowest free bits
         for (int b = 0; b < n && __builtin_popcountll(T) < M; b++) T |= uint64_t{1} << b;
         simulate(f, pending, T, full, exec);
+        if (exec.size() > static_cast<size_t>(kMaxPassOps)) exec.resize(kMaxPassOps); // a prefix stays valid
         std::vector<int> pass_ops = exec;
-        for (int i : pass_ops) done[i] = 1;
 
         // ---- rounds
         HostPass hp;
@@ -348,18 +410,23 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                 else next.push_back(i);
             }
             rem.swap(next);
+            if (hp.rounds.size() == static_cast<size_t>(kMaxPassRounds)) break; // rest waits for the next pass
         }
+        pass_ops.clear();
+        for (const auto &r : hp.rounds) pass_ops.insert(pass_ops.end(), r.begin(), r.end());
+        for (int i : pass_ops) done[i] = 1;
 
         // ---- encode the plan
         const size_t goff_n = size_t{1} << (M - LOW);
-        const size_t bytes = sizeof(PassHdr) + goff_n * sizeof(uint64_t) + hp.rounds.size() * sizeof(RoundHdr) +
-                             pass_ops.size() * sizeof(TileOp<T2>);
+        const size_t bytes = goff_n * sizeof(uint64_t);
         const size_t off = (arena.size() + 255) & ~size_t{255};
         arena.resize(off + bytes, 0);
-        PassHdr *hdr = reinterpret_cast<PassHdr *>(arena.data() + off);
-        uint64_t *goff = reinterpret_cast<uint64_t *>(arena.data() + off + sizeof(PassHdr));
-        RoundHdr *rh = reinterpret_cast<RoundHdr *>(goff + goff_n);
-        TileOp<T2> *top = reinterpret_cast<TileOp<T2> *>(rh + hp.rounds.size());
+        params.emplace_back();
+        std::memset(&params.back(), 0, sizeof(PassParams<T2>));
+        PassHdr *hdr = &params.back().hdr;
+        uint64_t *goff = reinterpret_cast<uint64_t *>(arena.data() + off);
+        RoundHdr *rh = params.back().rounds;
+        TileOp<T2> *top = params.back().ops;
         hdr->nrounds = static_cast<int>(hp.rounds.size());
         hdr->nops_total = static_cast<int>(pass_ops.size());
         hdr->ntiles = uint64_t{1} << (n - M);
@@ -401,12 +468,18 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                 t.cmask_l = to_local(op.cmask & T), t.cval_l = to_local(op.cval & T);
                 t.cmask_o = op.cmask & ~T, t.cval_o = op.cval & ~T;
                 if (op.kind == OP_PAIRS) {
-                    t.kind = 0;
+                    const cd *m = op.blocks[0].m;
+                    t.kind = TK_GENERAL;
+                    if (m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0)) t.kind = TK_SWAP;
+                    else if (m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0)
+                        t.kind = TK_REAL;
+                    else if (m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0)
+                        t.kind = TK_RXLIKE;
                     const int lp = local_of[op.tbits[0]];
                     t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
-                    for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(op.blocks[0].m[q].real(), op.blocks[0].m[q].imag());
+                    for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(m[q].real(), m[q].imag());
                 } else {
-                    t.kind = 1;
+                    t.kind = (fo.d[0] == cd(1.0)) ? TK_DIAG1 : TK_DIAG;
                     t.pmask_l = to_local(fo.pmask & T);
                     t.pmask_o = fo.pmask & ~T;
                     t.m[0] = mk<T2>(fo.d[0].real(), fo.d[0].imag());
@@ -416,6 +489,7 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
         }
         Step st;
         st.off = off;
+        st.params = params.size() - 1;
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
         st.nrounds = hdr->nrounds, st.nops = hdr->nops_total;
         steps.push_back(st);
@@ -426,13 +500,15 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
     constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
-    build_schedule<T2>(static_cast<int>(sv.n), sv.sm_count, ops, steps, arena);
+    std::vector<PassParams<T2>> params;
+    build_schedule<T2>(static_cast<int>(sv.n), sv.sm_count, ops, steps, arena, params);
     auto smem_bytes = (sizeof(T2) << M) + (sizeof(uint64_t) << (M - LOW));
     static bool attr_set_d = false, attr_set_f = false;
     bool &attr_set = sizeof(T2) == 16 ? attr_set_d : attr_set_f;
     if (!attr_set && !arena.empty()) {
         PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem_bytes)));
+        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     // ---- upload every pass plan once, then launch the whole schedule back to back
@@ -447,7 +523,8 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
             launch_op(sv, ops[st.op]);
             continue;
         }
-        tile_kernel<T2><<<st.grid, 1 << (M - kR), smem_bytes, sv.stream>>>(static_cast<T2 *>(sv.data), dplan + st.off);
+        tile_kernel<T2><<<st.grid, 1 << (M - kR), smem_bytes, sv.stream>>>(
+            static_cast<T2 *>(sv.data), reinterpret_cast<const uint64_t *>(dplan + st.off), params[st.params]);
         PLB_CUDA(cudaGetLastError());
         sv.launches++;
     }
@@ -458,8 +535,13 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
-    if (precision == 64) build_schedule<double2>(n, 148, ops, steps, arena);
-    else build_schedule<float2>(n, 148, ops, steps, arena);
+    if (precision == 64) {
+        std::vector<PassParams<double2>> params;
+        build_schedule<double2>(n, 148, ops, steps, arena, params);
+    } else {
+        std::vector<PassParams<float2>> params;
+        build_schedule<float2>(n, 148, ops, steps, arena, params);
+    }
     out[0] = out[1] = out[2] = out[3] = 0;
     for (const auto &s : steps) {
         if (s.op >= 0) out[1]++;

@@ -1,0 +1,37 @@
+"""BASELINE.json configs[4]: 24q hardware-efficient ansatz, 1000 params, 100-term Pauli Hamiltonian:
+adjoint Jacobian seconds on one B200 (+ optional lightning.qubit timing on the host cores)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pennylane_lightning_b200 as plb
+from pennylane_lightning_b200 import circuits
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+n_params = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+with_ref = len(sys.argv) > 3 and sys.argv[3] == "ref"
+ops, tp = circuits.hardware_efficient_ansatz(n, n_params, 99)
+co, words, wires = circuits.pauli_hamiltonian(n, 100, 99)
+out = {}
+for dt, tag in ((np.complex128, "c128"), (np.complex64, "c64")):
+    sv = plb.StateVector(n, dt)
+    ham = circuits.hamiltonian_observable(plb, co, words, wires)
+    sv.apply_ops(ops)
+    sv.sync()
+    t0 = time.perf_counter(); e = sv.expval(ham); t_e = time.perf_counter() - t0
+    t0 = time.perf_counter(); jac = sv.adjoint_jacobian([ham], ops, tp); t_j = time.perf_counter() - t0
+    t0 = time.perf_counter(); jac = sv.adjoint_jacobian([ham], ops, tp); t_j2 = time.perf_counter() - t0
+    S = (1 << n) * (16 if dt == np.complex128 else 8)
+    out[tag] = dict(expval=e, expval_s=t_e, adjoint_s=min(t_j, t_j2), eff_GBps=6 * S * n_params / min(t_j, t_j2) / 1e9,
+                    jac_norm=float(np.linalg.norm(jac)))
+    print(tag, out[tag], flush=True)
+    if with_ref and tag == "c128":
+        from oracle import lq_ref as R
+        rsv = R.StateVector(n, dt)
+        rham = circuits.hamiltonian_observable(R, co, words, wires, dtype=dt)
+        rsv.apply_ops(ops)
+        t0 = time.perf_counter(); rj = rsv.adjoint_jacobian([rham], ops, tp); t_r = time.perf_counter() - t0
+        err = float(np.max(np.abs(rj - jac)) / np.max(np.abs(rj)))
+        out["ref"] = dict(adjoint_s=t_r, cores=R.num_threads(), max_rel_err=err, expval=rsv.expval(rham))
+        print("ref", out["ref"], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open(f"gpurun_out/adjoint_{n}q_{n_params}.json", "w"))

@@ -1,6 +1,8 @@
 """Per-gate HBM bandwidth sweep (un-fused kernels), gate type x target index bit."""
 import json, sys
 import numpy as np, torch
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pennylane_lightning_b200 as plb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
