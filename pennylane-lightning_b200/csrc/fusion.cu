@@ -39,20 +39,30 @@ template <> struct TileCfg<float2> {
 // op kinds inside a tile pass
 enum : int {
     TK_GENERAL = 0, // complex 2x2 on register bit p
-    TK_DIAG = 1,    // phase m[parity]
-    TK_SWAP = 2,    // [[0,1],[1,0]] (PauliX / CNOT / Toffoli): pure register exchange, no flops
-    TK_REAL = 3,    // real 2x2 (RY, Hadamard)
-    TK_RXLIKE = 4,  // real diagonal, imaginary off-diagonal (RX)
-    TK_DIAG1 = 5,   // phase on the parity-1 half only (m[0] == 1)
+    TK_SWAP = 1,    // [[0,1],[1,0]] (PauliX / CNOT / Toffoli): pure register exchange, no flops
+    TK_REAL = 2,    // real 2x2 (RY, Hadamard)
+    TK_RXLIKE = 3,  // real diagonal, imaginary off-diagonal (RX)
+    TK_DIAG_T = 4,  // phase m[parity], parity bits on thread / outside bits only
+    TK_DIAG_R = 5,  // ... plus exactly one register bit p
+    TK_DIAG_G = 6,  // ... any register bits (per-amplitude select)
+    TK_DIAG1_T = 7, // as DIAG_T with m[0] == 1: only the parity-1 amplitudes are multiplied
+    TK_DIAG1_R = 8, // as DIAG_R with m[0] == 1
 };
-constexpr int kMaxPassOps = 256;
+constexpr int kMaxPassOps = 224;
 constexpr int kMaxPassRounds = 22;
 
+// Controls / parity masks are split on the host into a per-thread part (tile-local index bits that
+// are thread bits in this round) and a per-register part (16-bit patterns over the register index
+// u), so that the per-amplitude predicate is a single bit test on a compile-time position.
 template <typename T2> struct alignas(16) TileOp {
     int kind;
     int p;
-    uint32_t cmask_l, cval_l, pmask_l, pad;
-    uint64_t cmask_o, cval_o, pmask_o;
+    uint32_t cm_thr, cv_thr; // controls on thread bits (tile-local index space)
+    uint32_t pm_thr;         // parity mask on thread bits
+    uint32_t umask;          // bit u: register index u satisfies the register-bit controls
+    uint32_t upar;           // bit u: parity of u's register bits under the parity mask
+    uint32_t pad;
+    uint64_t cmask_o, cval_o, pmask_o; // bits outside the tile: uniform per tile
     T2 m[4];
 };
 struct alignas(16) RoundHdr {
@@ -76,16 +86,13 @@ template <typename T2> struct alignas(16) PassParams {
 __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
 
 template <typename T2, int P, int KIND>
-__device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t jbase,
-                                           const uint32_t *roff) {
+__device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active) {
     const T2 m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
-    const uint32_t cm = op.cmask_l, cv = op.cval_l;
 #pragma unroll
     for (int q = 0; q < (1 << (kR - 1)); q++) {
         const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
         const int u1 = u0 | (1 << P);
-        const uint32_t j = jbase | roff[u0];
-        if ((j & cm) == cv) {
+        if (active & (1u << u0)) {
             const T2 a = v[u0], b = v[u1];
             if constexpr (KIND == TK_SWAP) {
                 v[u0] = b, v[u1] = a;
@@ -104,24 +111,30 @@ __device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &o
     }
 }
 
-template <typename T2, int KIND>
-__device__ __forceinline__ void apply_pair_p(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t jbase,
-                                             const uint32_t *roff) {
-    switch (op.p) {
-    case 0:
-        apply_pair<T2, 0, KIND>(v, op, jbase, roff);
-        break;
-    case 1:
-        apply_pair<T2, 1, KIND>(v, op, jbase, roff);
-        break;
-    case 2:
-        apply_pair<T2, 2, KIND>(v, op, jbase, roff);
-        break;
-    default:
-        apply_pair<T2, 3, KIND>(v, op, jbase, roff);
-        break;
+template <typename T2, int P, bool ONE>
+__device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active, bool pt) {
+    if constexpr (ONE) {
+        const T2 d1 = op.m[1];
+#pragma unroll
+        for (int u = 0; u < (1 << kR); u++) {
+            const bool par = ((u >> P) & 1) ? !pt : pt;
+            if ((active & (1u << u)) && par) v[u] = cmul(v[u], d1);
+        }
+    } else {
+        const T2 da = pt ? op.m[1] : op.m[0], db = pt ? op.m[0] : op.m[1];
+#pragma unroll
+        for (int u = 0; u < (1 << kR); u++)
+            if (active & (1u << u)) v[u] = cmul(v[u], ((u >> P) & 1) ? db : da);
     }
 }
+
+#define PLB_SWITCH_P(CALL)                                                                               \
+    switch (op.p) {                                                                                      \
+    case 0: { constexpr int P = 0; CALL; } break;                                                        \
+    case 1: { constexpr int P = 1; CALL; } break;                                                        \
+    case 2: { constexpr int P = 2; CALL; } break;                                                        \
+    default: { constexpr int P = 3; CALL; } break;                                                       \
+    }
 
 template <typename T2>
 __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
@@ -132,19 +145,15 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T2 *tile = reinterpret_cast<T2 *>(smem_raw);
     uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(T2) << M));
-
-    const PassHdr *hdr = &pp.hdr;
-    const RoundHdr *rounds = pp.rounds;
-    const TileOp<T2> *ops = pp.ops;
     static_assert(sizeof(PassParams<T2>) <= 32764, "kernel parameter space");
 
     for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
     __syncthreads();
     const uint32_t tid = threadIdx.x;
-    const int nrounds = hdr->nrounds;
+    const int nrounds = pp.hdr.nrounds;
 
-    for (uint64_t t = blockIdx.x; t < hdr->ntiles; t += gridDim.x) {
-        const uint64_t base = insert_bits(t, hdr->tile_ins);
+    for (uint64_t t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
+        const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
         // ---- load the tile (coalesced 128-byte lines)
         {
             T2 v[NV];
@@ -159,62 +168,64 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
         __syncthreads();
         // ---- rounds
         for (int r = 0; r < nrounds; r++) {
-            const RoundHdr &rh = rounds[r];
+            const RoundHdr &rh = pp.rounds[r];
             uint32_t jbase = tid;
 #pragma unroll
             for (int i = 0; i < kR; i++) {
                 const uint32_t lm = rh.lowmask[i];
                 jbase = ((jbase & ~lm) << 1) | (jbase & lm);
             }
-            uint32_t roff[NV];
-#pragma unroll
-            for (int u = 0; u < NV; u++) roff[u] = rh.roff[u];
             T2 v[NV];
 #pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = tile[swz(jbase | roff[u])];
-            for (int k = 0; k < rh.nops; k++) {
-                const TileOp<T2> &op = ops[rh.first_op + k];
+            for (int u = 0; u < NV; u++) v[u] = tile[swz(jbase | rh.roff[u])];
+            const int k_end = rh.first_op + rh.nops;
+            for (int k = rh.first_op; k < k_end; k++) {
+                const TileOp<T2> &op = pp.ops[k];
                 if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
+                const uint32_t active = ((jbase & op.cm_thr) == op.cv_thr) ? op.umask : 0u;
                 switch (op.kind) {
                 case TK_GENERAL:
-                    apply_pair_p<T2, TK_GENERAL>(v, op, jbase, roff);
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_GENERAL>(v, op, active)));
                     break;
                 case TK_SWAP:
-                    apply_pair_p<T2, TK_SWAP>(v, op, jbase, roff);
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_SWAP>(v, op, active)));
                     break;
                 case TK_REAL:
-                    apply_pair_p<T2, TK_REAL>(v, op, jbase, roff);
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_REAL>(v, op, active)));
                     break;
                 case TK_RXLIKE:
-                    apply_pair_p<T2, TK_RXLIKE>(v, op, jbase, roff);
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_RXLIKE>(v, op, active)));
                     break;
-                case TK_DIAG1: {
-                    const uint32_t po = __popcll(base & op.pmask_o) & 1;
-                    const T2 d1 = op.m[1];
-                    const uint32_t cm = op.cmask_l, cv = op.cval_l, pm = op.pmask_l;
-#pragma unroll
-                    for (int u = 0; u < NV; u++) {
-                        const uint32_t j = jbase | roff[u];
-                        if ((j & cm) == cv && (((__popc(j & pm) & 1) ^ po) != 0)) v[u] = cmul(v[u], d1);
-                    }
-                } break;
                 default: {
-                    const uint32_t po = __popcll(base & op.pmask_o) & 1;
-                    const T2 d0 = op.m[0], d1 = op.m[1];
-                    const uint32_t cm = op.cmask_l, cv = op.cval_l, pm = op.pmask_l;
+                    const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
+                    if (op.kind == TK_DIAG_T) {
+                        const T2 d = pt ? op.m[1] : op.m[0];
 #pragma unroll
-                    for (int u = 0; u < NV; u++) {
-                        const uint32_t j = jbase | roff[u];
-                        if ((j & cm) == cv) {
-                            const uint32_t par = (__popc(j & pm) & 1) ^ po;
-                            v[u] = cmul(v[u], par ? d1 : d0);
+                        for (int u = 0; u < NV; u++)
+                            if (active & (1u << u)) v[u] = cmul(v[u], d);
+                    } else if (op.kind == TK_DIAG1_T) {
+                        if (pt) {
+                            const T2 d = op.m[1];
+#pragma unroll
+                            for (int u = 0; u < NV; u++)
+                                if (active & (1u << u)) v[u] = cmul(v[u], d);
                         }
+                    } else if (op.kind == TK_DIAG_R) {
+                        PLB_SWITCH_P((apply_diag_r<T2, P, false>(v, op, active, pt)));
+                    } else if (op.kind == TK_DIAG1_R) {
+                        PLB_SWITCH_P((apply_diag_r<T2, P, true>(v, op, active, pt)));
+                    } else {
+                        const uint32_t pb = pt ? ~op.upar : op.upar;
+                        const T2 d0 = op.m[0], d1 = op.m[1];
+#pragma unroll
+                        for (int u = 0; u < NV; u++)
+                            if (active & (1u << u)) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
                     }
                 } break;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < NV; u++) tile[swz(jbase | roff[u])] = v[u];
+            for (int u = 0; u < NV; u++) tile[swz(jbase | rh.roff[u])] = v[u];
             __syncthreads();
         }
         // ---- store the tile
@@ -465,8 +476,19 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                 const COp &op = ops[idx];
                 const FOp &fo = f[idx];
                 TileOp<T2> &t = top[op_cursor++];
-                t.cmask_l = to_local(op.cmask & T), t.cval_l = to_local(op.cval & T);
+                const uint32_t cm_l = to_local(op.cmask & T), cv_l = to_local(op.cval & T);
+                uint32_t rmask_l = 0;
+                for (int i = 0; i < kR; i++) rmask_l |= 1u << rl[i];
+                t.cm_thr = cm_l & ~rmask_l, t.cv_thr = cv_l & ~rmask_l;
                 t.cmask_o = op.cmask & ~T, t.cval_o = op.cval & ~T;
+                const uint32_t pm_l = (op.kind == OP_PAIRS) ? 0u : to_local(fo.pmask & T);
+                t.pm_thr = pm_l & ~rmask_l;
+                t.umask = 0, t.upar = 0;
+                for (int u = 0; u < (1 << kR); u++) {
+                    const uint32_t ro = rh[r].roff[u];
+                    if ((ro & cm_l) == (cv_l & rmask_l)) t.umask |= 1u << u;
+                    if (__builtin_popcount(ro & pm_l) & 1) t.upar |= 1u << u;
+                }
                 if (op.kind == OP_PAIRS) {
                     const cd *m = op.blocks[0].m;
                     t.kind = TK_GENERAL;
@@ -479,8 +501,15 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                     t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
                     for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(m[q].real(), m[q].imag());
                 } else {
-                    t.kind = (fo.d[0] == cd(1.0)) ? TK_DIAG1 : TK_DIAG;
-                    t.pmask_l = to_local(fo.pmask & T);
+                    const bool one = (fo.d[0] == cd(1.0));
+                    const uint32_t pr = pm_l & rmask_l;
+                    if (pr == 0) t.kind = one ? TK_DIAG1_T : TK_DIAG_T;
+                    else if (__builtin_popcount(pr) == 1) {
+                        t.kind = one ? TK_DIAG1_R : TK_DIAG_R;
+                        const int lp = __builtin_ctz(pr);
+                        t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
+                    } else
+                        t.kind = TK_DIAG_G;
                     t.pmask_o = fo.pmask & ~T;
                     t.m[0] = mk<T2>(fo.d[0].real(), fo.d[0].imag());
                     t.m[1] = mk<T2>(fo.d[1].real(), fo.d[1].imag());
