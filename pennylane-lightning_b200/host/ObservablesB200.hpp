@@ -1,0 +1,179 @@
+// Observable hierarchy of the B200 backend, mirroring core/observables/Observables.hpp:36-584
+// (Observable, NamedObsBase, HermitianObsBase, TensorProdObsBase, HamiltonianBase) and the LGPU
+// finals in lightning_gpu/observables/ObservablesGPU.hpp.  Each object owns a plb200_obs tree.
+#pragma once
+#include <complex>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "StateVectorB200.hpp"
+
+namespace Pennylane::LightningB200::Observables {
+
+template <class StateVectorT> class Observable {
+  public:
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    virtual ~Observable() {
+        if (h_) plb200_obs_destroy(h_);
+    }
+    Observable(const Observable &) = delete;
+    Observable &operator=(const Observable &) = delete;
+
+    // Apply the observable to the given state vector in place (Observables.hpp:63)
+    virtual void applyInPlace(StateVectorT &sv) const { PLB200_ABI(plb200_obs_apply(h_, sv.handle())); }
+    [[nodiscard]] virtual auto getObsName() const -> std::string = 0;
+    [[nodiscard]] virtual auto getWires() const -> std::vector<std::size_t> = 0;
+    [[nodiscard]] virtual auto getObs() const -> std::vector<std::shared_ptr<Observable<StateVectorT>>> { return {}; }
+    [[nodiscard]] virtual auto getCoeffs() const -> std::vector<PrecisionT> { return {}; }
+    [[nodiscard]] bool operator==(const Observable &other) const {
+        return typeid(*this) == typeid(other) && isEqual(other);
+    }
+    [[nodiscard]] bool operator!=(const Observable &other) const { return !(*this == other); }
+    [[nodiscard]] const plb200_obs *handle() const { return h_; }
+
+  protected:
+    Observable() = default;
+    [[nodiscard]] virtual bool isEqual(const Observable &other) const = 0;
+    plb200_obs *h_ = nullptr;
+};
+
+template <class StateVectorT> class NamedObs final : public Observable<StateVectorT> {
+  public:
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    NamedObs(std::string obs_name, std::vector<std::size_t> wires, std::vector<PrecisionT> params = {})
+        : obs_name_{std::move(obs_name)}, wires_{std::move(wires)}, params_{std::move(params)} {
+        const auto w = detail::to_i64(wires_);
+        const auto p = detail::to_f64(params_);
+        PLB200_ABI(plb200_obs_named(&this->h_, obs_name_.c_str(), w.data(), static_cast<int64_t>(w.size()), p.data(),
+                                    static_cast<int64_t>(p.size())));
+    }
+    [[nodiscard]] auto getObsName() const -> std::string override {
+        std::ostringstream s;
+        s << obs_name_ << "[";
+        for (std::size_t i = 0; i < wires_.size(); i++) s << (i ? ", " : "") << wires_[i];
+        s << "]";
+        return s.str();
+    }
+    [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
+
+  private:
+    [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
+        const auto &o = static_cast<const NamedObs &>(other);
+        return obs_name_ == o.obs_name_ && wires_ == o.wires_ && params_ == o.params_;
+    }
+    std::string obs_name_;
+    std::vector<std::size_t> wires_;
+    std::vector<PrecisionT> params_;
+};
+
+template <class StateVectorT> class HermitianObs final : public Observable<StateVectorT> {
+  public:
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    using ComplexT = typename StateVectorT::ComplexT;
+    using MatrixT = std::vector<ComplexT>;
+    HermitianObs(MatrixT matrix, std::vector<std::size_t> wires) : matrix_{std::move(matrix)}, wires_{std::move(wires)} {
+        PLB200_ABORT_IF(matrix_.size() != (std::size_t{1} << (2 * wires_.size())),
+                        "The size of matrix does not match with the given number of wires");
+        const auto w = detail::to_i64(wires_);
+        const auto m = detail::to_c128(matrix_.data(), matrix_.size());
+        PLB200_ABI(plb200_obs_hermitian(&this->h_, m.data(), w.data(), static_cast<int64_t>(w.size())));
+    }
+    [[nodiscard]] auto getMatrix() const -> const MatrixT & { return matrix_; }
+    [[nodiscard]] auto getObsName() const -> std::string override { return "Hermitian"; }
+    [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
+
+  private:
+    [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
+        const auto &o = static_cast<const HermitianObs &>(other);
+        return matrix_ == o.matrix_ && wires_ == o.wires_;
+    }
+    MatrixT matrix_;
+    std::vector<std::size_t> wires_;
+};
+
+template <class StateVectorT> class TensorProdObs final : public Observable<StateVectorT> {
+  public:
+    using ObsPtr = std::shared_ptr<Observable<StateVectorT>>;
+    explicit TensorProdObs(std::vector<ObsPtr> obs) : obs_{std::move(obs)} {
+        std::vector<const plb200_obs *> hs;
+        for (const auto &o : obs_) {
+            hs.push_back(o->handle());
+            const auto w = o->getWires();
+            all_wires_.insert(all_wires_.end(), w.begin(), w.end());
+        }
+        PLB200_ABI(plb200_obs_tensor(&this->h_, hs.data(), static_cast<int64_t>(hs.size())));
+    }
+    static auto create(std::initializer_list<ObsPtr> obs) -> std::shared_ptr<TensorProdObs> {
+        return std::make_shared<TensorProdObs>(std::vector<ObsPtr>(obs));
+    }
+    [[nodiscard]] auto getSize() const -> std::size_t { return obs_.size(); }
+    [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return all_wires_; }
+    [[nodiscard]] auto getObs() const -> std::vector<ObsPtr> override { return obs_; }
+    [[nodiscard]] auto getObsName() const -> std::string override {
+        std::ostringstream s;
+        for (std::size_t i = 0; i < obs_.size(); i++) s << (i ? " @ " : "") << obs_[i]->getObsName();
+        return s.str();
+    }
+
+  private:
+    [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
+        const auto &o = static_cast<const TensorProdObs &>(other);
+        if (obs_.size() != o.obs_.size()) return false;
+        for (std::size_t i = 0; i < obs_.size(); i++)
+            if (*obs_[i] != *o.obs_[i]) return false;
+        return true;
+    }
+    std::vector<ObsPtr> obs_;
+    std::vector<std::size_t> all_wires_;
+};
+
+template <class StateVectorT> class Hamiltonian final : public Observable<StateVectorT> {
+  public:
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    using ObsPtr = std::shared_ptr<Observable<StateVectorT>>;
+    Hamiltonian(std::vector<PrecisionT> coeffs, std::vector<ObsPtr> obs) : coeffs_{std::move(coeffs)}, obs_{std::move(obs)} {
+        PLB200_ABORT_IF(coeffs_.size() != obs_.size(), "coeffs and obs must have the same size");
+        std::vector<const plb200_obs *> hs;
+        for (const auto &o : obs_) hs.push_back(o->handle());
+        const auto c = detail::to_f64(coeffs_);
+        PLB200_ABI(plb200_obs_hamiltonian(&this->h_, c.data(), hs.data(), static_cast<int64_t>(hs.size())));
+    }
+    static auto create(std::initializer_list<PrecisionT> coeffs, std::initializer_list<ObsPtr> obs)
+        -> std::shared_ptr<Hamiltonian> {
+        return std::make_shared<Hamiltonian>(std::vector<PrecisionT>(coeffs), std::vector<ObsPtr>(obs));
+    }
+    [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override {
+        std::vector<std::size_t> all;
+        for (const auto &o : obs_)
+            for (auto w : o->getWires())
+                if (std::find(all.begin(), all.end(), w) == all.end()) all.push_back(w);
+        std::sort(all.begin(), all.end());
+        return all;
+    }
+    [[nodiscard]] auto getObs() const -> std::vector<ObsPtr> override { return obs_; }
+    [[nodiscard]] auto getCoeffs() const -> std::vector<PrecisionT> override { return coeffs_; }
+    [[nodiscard]] auto getObsName() const -> std::string override {
+        std::ostringstream s;
+        s << "Hamiltonian: { 'coeffs' : [";
+        for (std::size_t i = 0; i < coeffs_.size(); i++) s << (i ? ", " : "") << coeffs_[i];
+        s << "], 'observables' : [";
+        for (std::size_t i = 0; i < obs_.size(); i++) s << (i ? ", " : "") << obs_[i]->getObsName();
+        s << "]}";
+        return s.str();
+    }
+
+  private:
+    [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
+        const auto &o = static_cast<const Hamiltonian &>(other);
+        if (coeffs_ != o.coeffs_ || obs_.size() != o.obs_.size()) return false;
+        for (std::size_t i = 0; i < obs_.size(); i++)
+            if (*obs_[i] != *o.obs_[i]) return false;
+        return true;
+    }
+    std::vector<PrecisionT> coeffs_;
+    std::vector<ObsPtr> obs_;
+};
+
+} // namespace Pennylane::LightningB200::Observables
