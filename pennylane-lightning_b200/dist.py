@@ -1,0 +1,338 @@
+"""Distributed state vector: index bits sharded over the GPUs of one box, one process per GPU.
+
+Replaces the reference's MPI backends (lightning_gpu/StateVectorCudaMPI.hpp:1936-2243: swap — apply —
+swap back around every gate touching a global wire; lightning_kokkos/StateVectorKokkosMPI.hpp:747-1097:
+lazy wire permutation) with:
+
+* rank r holds the slab of amplitudes whose top g = log2(world) *physical* index bits equal r;
+* a persistent logical-wire -> physical-bit permutation kept on the host (never swapped back);
+* per op: all non-diagonal targets local -> plain local kernel(s); a control on a global bit ->
+  ranks whose bit mismatches skip, the others drop the control (no communication); a diagonal factor
+  on a global bit -> rank-dependent phase (no communication); otherwise an index-bit swap
+  (pack kernel -> NCCL send/recv between the two partner ranks -> unpack kernel; half a slab each way);
+* ops are collected into maximal local batches (ops on disjoint wires commute) which run through the
+  fused tile executor; swaps are chosen for the wires blocked ops wait for, evicting the local wires
+  whose next non-diagonal use is farthest away;
+* reductions: local kernel -> all_reduce(SUM) of fp64 scalars.
+
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is only plumbing; the local engine is
+libplb200 through the C ABI (`_capi.StateVector` on a torch-owned slab).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# gates that are "control (x) base": name -> (base gate, number of leading control wires)
+IMPLICIT_CTRL = {
+    "CNOT": ("PauliX", 1), "CY": ("PauliY", 1), "CZ": ("PauliZ", 1), "CRX": ("RX", 1), "CRY": ("RY", 1),
+    "CRZ": ("RZ", 1), "CRot": ("Rot", 1), "Toffoli": ("PauliX", 2), "CSWAP": ("SWAP", 1),
+    "ControlledPhaseShift": ("PhaseShift", 1),
+}
+
+
+def _diag_of(name, params, k, inverse):
+    """Diagonal of a diagonal base gate on k wires (wires[0] = most significant), or None."""
+    p = params
+    if name == "PauliZ":
+        d = np.array([1, -1], dtype=complex)
+    elif name == "S":
+        d = np.array([1, 1j])
+    elif name == "T":
+        d = np.array([1, np.exp(0.25j * np.pi)])
+    elif name == "PhaseShift":
+        d = np.array([1, np.exp(1j * p[0])])
+    elif name == "RZ":
+        d = np.array([np.exp(-0.5j * p[0]), np.exp(0.5j * p[0])])
+    elif name == "IsingZZ":
+        a, b = np.exp(-0.5j * p[0]), np.exp(0.5j * p[0])
+        d = np.array([a, b, b, a])
+    elif name == "MultiRZ":
+        par = np.array([bin(i).count("1") & 1 for i in range(1 << k)])
+        d = np.exp(-0.5j * p[0] * (1 - 2 * par))
+    elif name == "GlobalPhase":
+        d = np.full(1 << k, np.exp(-1j * p[0]))
+    elif name == "Identity":
+        d = np.ones(1 << k, dtype=complex)
+    else:
+        return None
+    return d.conj() if inverse else d
+
+
+def normalize_op(o):
+    """-> dict(base, targets, ctrl_wires, ctrl_values, params, inverse, matrix)"""
+    name = o["name"]
+    wires = list(o["wires"])
+    cw = list(o.get("ctrl_wires", ()))
+    cv = [bool(v) for v in o.get("ctrl_values", ())]
+    if name in IMPLICIT_CTRL:
+        base, nc = IMPLICIT_CTRL[name]
+        cw = cw + wires[:nc]
+        cv = cv + [True] * nc
+        wires = wires[nc:]
+        name = base
+    return dict(base=name, targets=wires, ctrl_wires=cw, ctrl_values=cv, params=list(o.get("params", ())),
+                inverse=bool(o.get("inverse", False)), matrix=o.get("matrix", None))
+
+
+class LocalEngine:
+    """GPU local engine: libplb200 on a torch-owned slab."""
+
+    def __init__(self, nloc, dtype, device):
+        import torch
+
+        from . import _capi
+
+        self.torch = torch
+        self.nloc = nloc
+        self.dtype = np.dtype(dtype)
+        tdt = torch.complex128 if self.dtype == np.complex128 else torch.complex64
+        self.slab = torch.zeros(1 << nloc, dtype=tdt, device=device)
+        self.sv = _capi.StateVector(nloc, dtype, device.index or 0, torch.cuda.current_stream(device).cuda_stream,
+                                    device_ptr=self.slab.data_ptr())
+        self._buf = None
+
+    def zero(self):
+        self.slab.zero_()
+
+    def set_amp(self, idx, val):
+        self.slab[idx] = val
+
+    def apply_ops(self, ops, fuse=True):
+        if ops:
+            self.sv.apply_ops(ops, fuse=fuse)
+
+    def apply_matrix(self, matrix, wires, ctrl_wires=(), ctrl_values=()):
+        self.sv.apply_matrix(matrix, wires, False, ctrl_wires, ctrl_values)
+
+    def buffers(self):
+        if self._buf is None:
+            half = 1 << (self.nloc - 1)
+            self._buf = (self.torch.empty(half, dtype=self.slab.dtype, device=self.slab.device),
+                         self.torch.empty(half, dtype=self.slab.dtype, device=self.slab.device))
+        return self._buf
+
+    def pack_bit(self, bit, keep, buf):
+        from . import _capi
+        import ctypes as C
+
+        _capi._check(_capi.lib().plb200_sv_pack_bit(self.sv._h, C.c_int64(bit), int(keep), C.c_void_p(buf.data_ptr())))
+
+    def unpack_bit(self, bit, keep, buf):
+        from . import _capi
+        import ctypes as C
+
+        _capi._check(_capi.lib().plb200_sv_unpack_bit(self.sv._h, C.c_int64(bit), int(keep),
+                                                      C.c_void_p(buf.data_ptr())))
+
+    def z_sums(self, local_wires):
+        """un-normalised sum_i (+-)|a_i|^2 for Z on each local wire, plus the local norm^2 (last)."""
+        words = ["Z"] * len(local_wires) + ["I"]
+        wires = [[w] for w in local_wires] + [[0]]
+        return self.sv.expval_pauli_words_each(words, wires)
+
+    def host_state(self):
+        return self.slab.cpu().numpy()
+
+    @property
+    def kernel_launches(self):
+        return self.sv.kernel_launches
+
+
+class DistStateVector:
+    def __init__(self, num_qubits, dtype=np.complex128, engine_factory=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.dist, self.torch = dist, torch
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.g = int(np.log2(self.world))
+        if (1 << self.g) != self.world:
+            raise ValueError("world size must be a power of two")
+        self.n = num_qubits
+        self.nloc = num_qubits - self.g
+        if self.nloc < 1:
+            raise ValueError("too few qubits for this many ranks")
+        self.dtype = np.dtype(dtype)
+        if engine_factory is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+            self.engine = LocalEngine(self.nloc, dtype, device)
+        else:
+            self.engine = engine_factory(self.nloc, dtype)
+        self.n_swaps = 0
+        self.swap_bytes = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ bookkeeping
+    def reset(self):
+        # wire w -> physical bit (wire 0 = most significant physical bit)
+        self.phys = [self.n - 1 - w for w in range(self.n)]
+        self.engine.zero()
+        if self.rank == 0:
+            self.engine.set_amp(0, 1.0)
+
+    def _is_global(self, w):
+        return self.phys[w] >= self.nloc
+
+    def _rank_bit(self, w):
+        return (self.rank >> (self.phys[w] - self.nloc)) & 1
+
+    def _lw(self, w):
+        """local wire index (engine convention: wire 0 = most significant local bit)"""
+        return self.nloc - 1 - self.phys[w]
+
+    @property
+    def kernel_launches(self):
+        return self.engine.kernel_launches
+
+    # ------------------------------------------------------------------ op classification
+    def _localize(self, op):
+        """Try to express a normalised op on the local slab without communication.
+        Returns ('skip', None) | ('ops', [engine op dicts]) | ('matrix', (matrix, wires, cw, cv)) |
+        ('blocked', set of global wires that must become local)."""
+        cw, cv = [], []
+        for w, v in zip(op["ctrl_wires"], op["ctrl_values"]):
+            if self._is_global(w):
+                if self._rank_bit(w) != int(v):
+                    return "skip", None
+            else:
+                cw.append(w), cv.append(v)
+        tg = [w for w in op["targets"] if self._is_global(w)]
+        if not tg and op["base"] != "GlobalPhase":
+            o = dict(name=op["base"], wires=[self._lw(w) for w in op["targets"]], params=op["params"],
+                     inverse=op["inverse"], ctrl_wires=[self._lw(w) for w in cw], ctrl_values=cv)
+            if op["matrix"] is not None:
+                o["matrix"] = op["matrix"]
+            return "ops", [o]
+        d = None if op["matrix"] is not None else _diag_of(op["base"], op["params"], len(op["targets"]), op["inverse"])
+        if d is None:
+            return "blocked", set(tg)
+        # diagonal: fix the global target bits to this rank's values
+        k = len(op["targets"])
+        d = d.reshape((2,) * k) if k else d.reshape(())
+        sl = tuple(self._rank_bit(w) if self._is_global(w) else slice(None) for w in op["targets"])
+        d = np.asarray(d[sl] if k else d).reshape(-1)
+        lt = [w for w in op["targets"] if not self._is_global(w)]
+        if op["base"] == "GlobalPhase":
+            lt, d = [], d[:1]
+        if not lt:
+            # scalar on the (controlled) subspace: 2x2 scalar matrix on any free local wire
+            free = next(w for w in range(self.n) if not self._is_global(w) and w not in cw)
+            if abs(d[0] - 1.0) == 0.0:
+                return "skip", None
+            return "matrix", (np.diag([d[0], d[0]]), [self._lw(free)], [self._lw(w) for w in cw], cv)
+        return "matrix", (np.diag(d), [self._lw(w) for w in lt], [self._lw(w) for w in cw], cv)
+
+    @staticmethod
+    def _all_wires(op):
+        return set(op["targets"]) | set(op["ctrl_wires"])
+
+    def _nondiag_targets(self, op):
+        if op["matrix"] is None and _diag_of(op["base"], op["params"], len(op["targets"]), op["inverse"]) is not None:
+            return set()
+        return set(op["targets"])
+
+    # ------------------------------------------------------------------ index-bit swap
+    def _swap(self, gw, lw):
+        """Exchange global wire gw with local wire lw (persistent: only the permutation remembers)."""
+        dist, torch = self.dist, self.torch
+        gb, lb = self.phys[gw], self.phys[lw]
+        r = gb - self.nloc
+        partner = self.rank ^ (1 << r)
+        keep = (self.rank >> r) & 1  # this rank keeps local bit == its rank bit
+        send, recv = self.engine.buffers()
+        self.engine.pack_bit(lb, keep, send)
+        ops = [dist.P2POp(dist.isend, send, partner, group=self.group),
+               dist.P2POp(dist.irecv, recv, partner, group=self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.engine.unpack_bit(lb, keep, recv)
+        self.phys[gw], self.phys[lw] = lb, gb
+        self.n_swaps += 1
+        self.swap_bytes += send.numel() * send.element_size()
+
+    # ------------------------------------------------------------------ tape execution
+    def apply_ops(self, ops, fuse=True):
+        pending = [normalize_op(o) for o in ops]
+        while pending:
+            batch, rest, blocked, need = [], [], set(), []
+            for op in pending:
+                wires = self._all_wires(op)
+                if wires & blocked:
+                    blocked |= wires
+                    rest.append(op)
+                    continue
+                kind, payload = self._localize(op)
+                if kind == "blocked":
+                    blocked |= wires
+                    rest.append(op)
+                    for w in sorted(payload):
+                        if w not in need:
+                            need.append(w)
+                elif kind == "ops":
+                    batch += payload
+                elif kind == "matrix":
+                    m, w, cw, cv = payload
+                    batch.append(dict(name="Matrix", wires=w, params=[], inverse=False, ctrl_wires=cw, ctrl_values=cv,
+                                      matrix=m))
+            self.engine.apply_ops(batch, fuse=fuse)
+            if rest:
+                self._make_local(need, rest)
+            pending = rest
+
+    def _make_local(self, need, rest):
+        """Swap the needed global wires in, evicting local wires with the farthest next non-diagonal use."""
+        nxt = {}
+        for i, op in enumerate(rest):
+            for w in self._nondiag_targets(op):
+                nxt.setdefault(w, i)
+        need = need[: self.g]
+        cand = [w for w in range(self.n) if not self._is_global(w) and w not in need]
+        # never evict the three lowest local bits' wires first: high local bits pack in full 128-B lines
+        cand.sort(key=lambda w: (nxt.get(w, 1 << 30), self.phys[w]), reverse=True)
+        for gw, lw in zip(need, cand):
+            self._swap(gw, lw)
+
+    # ------------------------------------------------------------------ measurements
+    def _allreduce(self, arr):
+        t = self.torch.as_tensor(np.asarray(arr, dtype=np.float64))
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def expval_z_all(self):
+        """<Z_w> for every wire (and the norm as a by-product): local reduction + all_reduce."""
+        local = [w for w in range(self.n) if not self._is_global(w)]
+        sums = np.asarray(self.engine.z_sums([self._lw(w) for w in local]))
+        norm_local = sums[-1]
+        out = np.zeros(self.n + 1)
+        for w, s in zip(local, sums[:-1]):
+            out[w] = s
+        for w in range(self.n):
+            if self._is_global(w):
+                out[w] = (1 - 2 * self._rank_bit(w)) * norm_local
+        out[self.n] = norm_local
+        out = self._allreduce(out)
+        self.last_norm2 = float(out[self.n])
+        return out[: self.n]
+
+    def norm2(self):
+        self.expval_z_all()
+        return self.last_norm2
+
+    def gather_state(self):
+        """Full state in logical wire order on every rank (tests, small n only)."""
+        loc = np.ascontiguousarray(self.engine.host_state())
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, loc, group=self.group)
+        full = np.zeros(1 << self.n, dtype=loc.dtype)
+        idx = np.arange(1 << self.n, dtype=np.int64)
+        pidx = np.zeros_like(idx)
+        for w in range(self.n):
+            bit = (idx >> (self.n - 1 - w)) & 1
+            pidx |= bit << self.phys[w]
+        stacked = np.concatenate(parts)
+        full[:] = stacked[pidx]
+        return full

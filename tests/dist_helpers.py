@@ -1,0 +1,135 @@
+"""Helpers for the multi-rank tests: a numpy local engine (test infrastructure, built on the oracle)
+so that the sharding/permutation/swap-scheduling host logic of dist.py runs on CPU under gloo."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+class NumpyEngine:
+    def __init__(self, nloc, dtype):
+        import torch
+        from oracle import np_oracle
+
+        self.torch = torch
+        self.nloc = nloc
+        self.sv = np_oracle.StateVector(nloc, dtype)
+        self.sv.state[:] = 0
+        self.launches = 0
+
+    def zero(self):
+        self.sv.state[:] = 0
+
+    def set_amp(self, idx, val):
+        self.sv.state[idx] = val
+
+    def apply_ops(self, ops, fuse=True):
+        self.sv.apply_ops(ops)
+        self.launches += len(ops)
+
+    def buffers(self):
+        half = 1 << (self.nloc - 1)
+        dt = self.torch.complex128 if self.sv.dtype == np.complex128 else self.torch.complex64
+        return self.torch.empty(half, dtype=dt), self.torch.empty(half, dtype=dt)
+
+    def _sel(self, bit, keep):
+        idx = np.arange(1 << self.nloc)
+        return idx[((idx >> bit) & 1) != keep]
+
+    def pack_bit(self, bit, keep, buf):
+        buf.copy_(self.torch.from_numpy(self.sv.state[self._sel(bit, keep)].copy()))
+
+    def unpack_bit(self, bit, keep, buf):
+        self.sv.state[self._sel(bit, keep)] = buf.numpy()
+
+    def z_sums(self, local_wires):
+        p = np.abs(self.sv.state.astype(np.complex128)) ** 2
+        idx = np.arange(1 << self.nloc)
+        out = [float(np.sum(p * (1 - 2 * ((idx >> (self.nloc - 1 - w)) & 1)))) for w in local_wires]
+        return out + [float(p.sum())]
+
+    def host_state(self):
+        return self.sv.state.copy()
+
+    @property
+    def kernel_launches(self):
+        return self.launches
+
+
+def mixed_circuit(n, seed, depth=4):
+    """config-4 family plus gates that exercise every classification branch of dist.py."""
+    from pennylane_lightning_b200 import circuits
+
+    rng = np.random.default_rng(seed)
+    ops = circuits.random_circuit(n, depth, seed)
+    extra = []
+    for _ in range(3 * n):
+        r = rng.random()
+        p = [int(x) for x in rng.permutation(n)]
+        if r < 0.15:
+            extra.append(circuits.op("Toffoli", p[:3]))
+        elif r < 0.3:
+            extra.append(circuits.op("ControlledPhaseShift", p[:2], [rng.uniform(0, 6)]))
+        elif r < 0.45:
+            extra.append(circuits.op("IsingZZ", p[:2], [rng.uniform(0, 6)], inverse=True))
+        elif r < 0.55:
+            extra.append(circuits.op("MultiRZ", p[:3], [rng.uniform(0, 6)]))
+        elif r < 0.65:
+            extra.append(circuits.op("SWAP", p[:2]))
+        elif r < 0.75:
+            extra.append(circuits.op("RY", p[:1], [rng.uniform(0, 6)], ctrl_wires=p[1:3], ctrl_values=[True, False]))
+        elif r < 0.85:
+            extra.append(circuits.op("GlobalPhase", p[:1], [rng.uniform(0, 6)]))
+        elif r < 0.92:
+            extra.append(circuits.op("CSWAP", p[:3]))
+        else:
+            extra.append(circuits.op("Hadamard", p[:1]))
+    out = []
+    for i, o in enumerate(ops):
+        out.append(o)
+        if i % 3 == 0 and extra:
+            out.append(extra.pop())
+    return out + extra
+
+
+def worker(rank, world, n, seed, port, backend, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    from pennylane_lightning_b200.dist import DistStateVector
+
+    try:
+        factory = NumpyEngine if backend == "gloo" else None
+        if backend == "nccl":
+            torch.cuda.set_device(rank)
+        sv = DistStateVector(n, np.complex128, engine_factory=factory)
+        ops = mixed_circuit(n, seed)
+        sv.apply_ops(ops, fuse=True)
+        z = sv.expval_z_all()
+        full = sv.gather_state()
+        if rank == 0:
+            q.put(dict(state=full, z=z, norm2=sv.last_norm2, swaps=sv.n_swaps))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_ranks(world, n, seed, backend="gloo", port=29611):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, world, n, seed, port, backend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    return res
