@@ -85,16 +85,14 @@ template <typename T2> struct alignas(16) PassParams {
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
 
-// PRED = false: every amplitude of this thread is subject to the op (no controls, or all control bits
-// satisfied): straight-line code without predicates.  PRED = true: per-amplitude bit test.
-template <typename T2, int P, int KIND, bool PRED>
+template <typename T2, int P, int KIND>
 __device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active) {
     const T2 m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
 #pragma unroll
     for (int q = 0; q < (1 << (kR - 1)); q++) {
         const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
         const int u1 = u0 | (1 << P);
-        if (!PRED || (active & (1u << u0))) {
+        if (active & (1u << u0)) {
             const T2 a = v[u0], b = v[u1];
             if constexpr (KIND == TK_SWAP) {
                 v[u0] = b, v[u1] = a;
@@ -113,32 +111,21 @@ __device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &o
     }
 }
 
-template <typename T2, int P, bool ONE, bool PRED>
+template <typename T2, int P, bool ONE>
 __device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active, bool pt) {
     if constexpr (ONE) {
         const T2 d1 = op.m[1];
-        if (pt) {
 #pragma unroll
-            for (int u = 0; u < (1 << kR); u++)
-                if (!((u >> P) & 1) && (!PRED || (active & (1u << u)))) v[u] = cmul(v[u], d1);
-        } else {
-#pragma unroll
-            for (int u = 0; u < (1 << kR); u++)
-                if (((u >> P) & 1) && (!PRED || (active & (1u << u)))) v[u] = cmul(v[u], d1);
+        for (int u = 0; u < (1 << kR); u++) {
+            const bool par = ((u >> P) & 1) ? !pt : pt;
+            if ((active & (1u << u)) && par) v[u] = cmul(v[u], d1);
         }
     } else {
         const T2 da = pt ? op.m[1] : op.m[0], db = pt ? op.m[0] : op.m[1];
 #pragma unroll
         for (int u = 0; u < (1 << kR); u++)
-            if (!PRED || (active & (1u << u))) v[u] = cmul(v[u], ((u >> P) & 1) ? db : da);
+            if (active & (1u << u)) v[u] = cmul(v[u], ((u >> P) & 1) ? db : da);
     }
-}
-
-template <typename T2, bool PRED>
-__device__ __forceinline__ void apply_scalar(T2 (&v)[1 << kR], T2 d, uint32_t active) {
-#pragma unroll
-    for (int u = 0; u < (1 << kR); u++)
-        if (!PRED || (active & (1u << u))) v[u] = cmul(v[u], d);
 }
 
 #define PLB_SWITCH_P(CALL)                                                                               \
@@ -149,45 +136,8 @@ __device__ __forceinline__ void apply_scalar(T2 (&v)[1 << kR], T2 d, uint32_t ac
     default: { constexpr int P = 3; CALL; } break;                                                       \
     }
 
-template <typename T2, bool PRED>
-__device__ __forceinline__ void apply_op(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active, uint32_t jbase,
-                                         uint64_t base) {
-    switch (op.kind) {
-    case TK_GENERAL:
-        PLB_SWITCH_P((apply_pair<T2, P, TK_GENERAL, PRED>(v, op, active)));
-        break;
-    case TK_SWAP:
-        PLB_SWITCH_P((apply_pair<T2, P, TK_SWAP, PRED>(v, op, active)));
-        break;
-    case TK_REAL:
-        PLB_SWITCH_P((apply_pair<T2, P, TK_REAL, PRED>(v, op, active)));
-        break;
-    case TK_RXLIKE:
-        PLB_SWITCH_P((apply_pair<T2, P, TK_RXLIKE, PRED>(v, op, active)));
-        break;
-    default: {
-        const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
-        if (op.kind == TK_DIAG_T) {
-            apply_scalar<T2, PRED>(v, pt ? op.m[1] : op.m[0], active);
-        } else if (op.kind == TK_DIAG1_T) {
-            if (pt) apply_scalar<T2, PRED>(v, op.m[1], active);
-        } else if (op.kind == TK_DIAG_R) {
-            PLB_SWITCH_P((apply_diag_r<T2, P, false, PRED>(v, op, active, pt)));
-        } else if (op.kind == TK_DIAG1_R) {
-            PLB_SWITCH_P((apply_diag_r<T2, P, true, PRED>(v, op, active, pt)));
-        } else {
-            const uint32_t pb = pt ? ~op.upar : op.upar;
-            const T2 d0 = op.m[0], d1 = op.m[1];
-#pragma unroll
-            for (int u = 0; u < (1 << kR); u++)
-                if (!PRED || (active & (1u << u))) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
-        }
-    } break;
-    }
-}
-
 template <typename T2>
-__global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR), 2)
+__global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
     tile_kernel(T2 *__restrict__ sv, const uint64_t *__restrict__ goff_g, const __grid_constant__ PassParams<T2> pp) {
     constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
     constexpr int NT = 1 << (M - kR);
@@ -233,8 +183,46 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR), 2)
                 const TileOp<T2> &op = pp.ops[k];
                 if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
                 const uint32_t active = ((jbase & op.cm_thr) == op.cv_thr) ? op.umask : 0u;
-                if (active == 0xFFFFu) apply_op<T2, false>(v, op, active, jbase, base);
-                else if (active != 0u) apply_op<T2, true>(v, op, active, jbase, base);
+                switch (op.kind) {
+                case TK_GENERAL:
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_GENERAL>(v, op, active)));
+                    break;
+                case TK_SWAP:
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_SWAP>(v, op, active)));
+                    break;
+                case TK_REAL:
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_REAL>(v, op, active)));
+                    break;
+                case TK_RXLIKE:
+                    PLB_SWITCH_P((apply_pair<T2, P, TK_RXLIKE>(v, op, active)));
+                    break;
+                default: {
+                    const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
+                    if (op.kind == TK_DIAG_T) {
+                        const T2 d = pt ? op.m[1] : op.m[0];
+#pragma unroll
+                        for (int u = 0; u < NV; u++)
+                            if (active & (1u << u)) v[u] = cmul(v[u], d);
+                    } else if (op.kind == TK_DIAG1_T) {
+                        if (pt) {
+                            const T2 d = op.m[1];
+#pragma unroll
+                            for (int u = 0; u < NV; u++)
+                                if (active & (1u << u)) v[u] = cmul(v[u], d);
+                        }
+                    } else if (op.kind == TK_DIAG_R) {
+                        PLB_SWITCH_P((apply_diag_r<T2, P, false>(v, op, active, pt)));
+                    } else if (op.kind == TK_DIAG1_R) {
+                        PLB_SWITCH_P((apply_diag_r<T2, P, true>(v, op, active, pt)));
+                    } else {
+                        const uint32_t pb = pt ? ~op.upar : op.upar;
+                        const T2 d0 = op.m[0], d1 = op.m[1];
+#pragma unroll
+                        for (int u = 0; u < NV; u++)
+                            if (active & (1u << u)) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
+                    }
+                } break;
+                }
             }
 #pragma unroll
             for (int u = 0; u < NV; u++) tile[swz(jbase | rh.roff[u])] = v[u];
