@@ -220,7 +220,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = n_gates * args.steps / (ms * 1e-3)
+    # units all ranks processed / time: every rank applies every gate of the tape to its own
+    # 2^LOCAL_QUBITS-amplitude slab, so the job processes world * n_gates slab-gates per step
+    # (identical to plain gates/s at N=1).
+    value = world * n_gates * args.steps / (ms * 1e-3)
 
     # ---- end-to-end through the public call sequence, host buffers ----------------------
     e2e_steps = max(1, min(args.steps, 3))
@@ -241,7 +244,7 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = n_gates * e2e_steps / e2e_s
+    e2e_value = world * n_gates * e2e_steps / e2e_s
 
     # ---- per-kernel roofline (live CUDA events per launch, un-fused kernels) ------------
     roofline = None
@@ -296,7 +299,14 @@ def run_ours(args):
                                    f"{nloc} local qubits per GPU",
                        "qubits": n, "gates": n_gates, "fused": fuse, "hbm_passes_per_step": stats[1],
                        "l2": "state (16 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"index-bit sharding over {world} GPU(s)"},
+                       "parallelism": f"index-bit sharding over {world} GPU(s)",
+                       "value_definition": "ranks x gates / time: each rank applies every gate to its own "
+                                           f"2^{nloc}-amplitude slab (= plain gates/s at N=1)",
+                       "circuit_gates_per_s": n_gates * args.steps / (ms * 1e-3),
+                       "index_bit_swaps_per_step": (sv.n_swaps // max(1, args.warmup + args.steps + e2e_steps))
+                       if world > 1 else 0,
+                       "nvlink_bytes_per_swap_per_gpu": (sv.swap_bytes // max(1, sv.n_swaps)) if world > 1 and
+                       sv.n_swaps else 0},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tape_bytes,
                     "d2h_bytes_per_step": 8 * n, "steps": e2e_steps,
