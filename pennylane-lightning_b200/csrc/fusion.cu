@@ -22,7 +22,10 @@ namespace plb200 {
 
 namespace {
 
-constexpr int kR = 4;       // register bits per round (16 amplitudes per thread)
+#ifndef PLB_KR
+#define PLB_KR 4
+#endif
+constexpr int kR = PLB_KR; // register bits per round (2^kR amplitudes per thread)
 constexpr int kMaxRoundOps = 4096;
 
 template <typename T2> struct TileCfg;
@@ -132,8 +135,8 @@ __device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << kR], const TileOp<T2> 
     switch (op.p) {                                                                                      \
     case 0: { constexpr int P = 0; CALL; } break;                                                        \
     case 1: { constexpr int P = 1; CALL; } break;                                                        \
-    case 2: { constexpr int P = 2; CALL; } break;                                                        \
-    default: { constexpr int P = 3; CALL; } break;                                                       \
+    case 2: { constexpr int P = (kR > 2 ? 2 : kR - 1); CALL; } break;                                                        \
+    default: { constexpr int P = (kR > 3 ? 3 : kR - 1); CALL; } break;                                                       \
     }
 
 template <typename T2>
