@@ -205,6 +205,12 @@ int plb200_sv_unpack_bit(plb200_sv *sv, int64_t bit, int keep, const void *buf);
 int plb200_sv_swap_bit_peer(plb200_sv *sv, int64_t bit, int keep, void *peer_device_ptr,
                             int do_half);
 
+/* CUDA IPC plumbing for the peer path (one process per GPU): export the slab of `sv` as a 64-byte
+ * handle, map a peer's slab into this process (peer access over NVLink is enabled lazily), unmap. */
+int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64);
+int plb200_ipc_open(const unsigned char *handle64, int device, void **peer_ptr);
+int plb200_ipc_close(void *peer_ptr, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -878,4 +878,28 @@ int plb200_sv_swap_bit_peer(plb200_sv *sv, int64_t bit, int keep, void *peer, in
     ABI_CATCH
 }
 
+int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64) {
+    ABI_TRY
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    sv->s.set_device();
+    cudaIpcMemHandle_t h;
+    PLB_CUDA(cudaIpcGetMemHandle(&h, sv->s.data));
+    std::memcpy(handle64, &h, 64);
+    ABI_CATCH
+}
+int plb200_ipc_open(const unsigned char *handle64, int device, void **peer_ptr) {
+    ABI_TRY
+    PLB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    PLB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ABI_CATCH
+}
+int plb200_ipc_close(void *peer_ptr, int device) {
+    ABI_TRY
+    PLB_CUDA(cudaSetDevice(device));
+    PLB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    ABI_CATCH
+}
+
 } // extern "C"

@@ -75,7 +75,7 @@ def normalize_op(o):
 
 
 class LocalEngine:
-    """GPU local engine: libplb200 on a torch-owned slab."""
+    """GPU local engine: libplb200 on its own cudaMalloc'ed slab (IPC-exportable for the peer path)."""
 
     def __init__(self, nloc, dtype, device):
         import torch
@@ -85,17 +85,48 @@ class LocalEngine:
         self.torch = torch
         self.nloc = nloc
         self.dtype = np.dtype(dtype)
-        tdt = torch.complex128 if self.dtype == np.complex128 else torch.complex64
-        self.slab = torch.zeros(1 << nloc, dtype=tdt, device=device)
-        self.sv = _capi.StateVector(nloc, dtype, device.index or 0, torch.cuda.current_stream(device).cuda_stream,
-                                    device_ptr=self.slab.data_ptr())
+        self.device = device
+        self.tdt = torch.complex128 if self.dtype == np.complex128 else torch.complex64
+        self.sv = _capi.StateVector(nloc, dtype, device.index or 0, torch.cuda.current_stream(device).cuda_stream)
         self._buf = None
+        self.peers = {}
 
     def zero(self):
-        self.slab.zero_()
+        self.sv.set_state_indices([], [])
 
     def set_amp(self, idx, val):
-        self.slab[idx] = val
+        self.sv.set_state_indices([idx], [val])
+
+    # ---- peer (CUDA IPC over NVLink) plumbing
+    def ipc_handle(self):
+        import ctypes as C
+
+        from . import _capi
+
+        buf = (C.c_ubyte * 64)()
+        _capi._check(_capi.lib().plb200_sv_ipc_handle(self.sv._h, buf))
+        return bytes(buf)
+
+    def open_peer(self, rank, handle):
+        import ctypes as C
+
+        from . import _capi
+
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _capi._check(_capi.lib().plb200_ipc_open(buf, self.device.index or 0, C.byref(ptr)))
+        self.peers[rank] = ptr.value
+
+    def swap_bit_peer(self, bit, keep, partner, half):
+        import ctypes as C
+
+        from . import _capi
+
+        _capi._check(_capi.lib().plb200_sv_swap_bit_peer(self.sv._h, C.c_int64(bit), int(keep),
+                                                         C.c_void_p(self.peers[partner]), int(half)))
+
+    def sync(self):
+        self.sv.sync()
 
     def apply_ops(self, ops, fuse=True):
         if ops:
@@ -107,8 +138,8 @@ class LocalEngine:
     def buffers(self):
         if self._buf is None:
             half = 1 << (self.nloc - 1)
-            self._buf = (self.torch.empty(half, dtype=self.slab.dtype, device=self.slab.device),
-                         self.torch.empty(half, dtype=self.slab.dtype, device=self.slab.device))
+            self._buf = (self.torch.empty(half, dtype=self.tdt, device=self.device),
+                         self.torch.empty(half, dtype=self.tdt, device=self.device))
         return self._buf
 
     def pack_bit(self, bit, keep, buf):
@@ -131,7 +162,7 @@ class LocalEngine:
         return self.sv.expval_pauli_words_each(words, wires)
 
     def host_state(self):
-        return self.slab.cpu().numpy()
+        return self.sv.get_state()
 
     @property
     def kernel_launches(self):
@@ -139,7 +170,7 @@ class LocalEngine:
 
 
 class DistStateVector:
-    def __init__(self, num_qubits, dtype=np.complex128, engine_factory=None, group=None):
+    def __init__(self, num_qubits, dtype=np.complex128, engine_factory=None, group=None, swap="auto"):
         import torch
         import torch.distributed as dist
 
@@ -162,6 +193,17 @@ class DistStateVector:
             self.engine = engine_factory(self.nloc, dtype)
         self.n_swaps = 0
         self.swap_bytes = 0
+        # swap transport: "peer" = in-place exchange over NVLink peer memory (CUDA IPC, no staging buffers:
+        # a 33-qubit c128 slab is 128 GiB and leaves no room for them); "nccl" = pack -> send/recv -> unpack.
+        self.swap_mode = swap
+        if swap == "auto":
+            self.swap_mode = "peer" if hasattr(self.engine, "ipc_handle") else "nccl"
+        if self.swap_mode == "peer":
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.engine.ipc_handle(), group=group)
+            for r in range(self.world):
+                if r != self.rank and bin(r ^ self.rank).count("1") == 1:
+                    self.engine.open_peer(r, handles[r])
         self.reset()
 
     # ------------------------------------------------------------------ bookkeeping
@@ -241,6 +283,17 @@ class DistStateVector:
         r = gb - self.nloc
         partner = self.rank ^ (1 << r)
         keep = (self.rank >> r) & 1  # this rank keeps local bit == its rank bit
+        if self.swap_mode == "peer":
+            # both partners exchange half of the pair range each, in place, with 128-bit peer loads/stores
+            self.engine.sync()
+            dist.barrier(group=self.group)
+            self.engine.swap_bit_peer(lb, keep, partner, 1 + keep)
+            self.engine.sync()
+            dist.barrier(group=self.group)
+            self.phys[gw], self.phys[lw] = lb, gb
+            self.n_swaps += 1
+            self.swap_bytes += (1 << (self.nloc - 1)) * self.dtype.itemsize
+            return
         send, recv = self.engine.buffers()
         self.engine.pack_bit(lb, keep, send)
         ops = [dist.P2POp(dist.isend, send, partner, group=self.group),

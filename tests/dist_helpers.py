@@ -97,7 +97,7 @@ def mixed_circuit(n, seed, depth=4):
     return out + extra
 
 
-def worker(rank, world, n, seed, port, backend, q):
+def worker(rank, world, n, seed, port, backend, q, swap="auto"):
     import torch
     import torch.distributed as dist
 
@@ -110,7 +110,7 @@ def worker(rank, world, n, seed, port, backend, q):
         factory = NumpyEngine if backend == "gloo" else None
         if backend == "nccl":
             torch.cuda.set_device(rank)
-        sv = DistStateVector(n, np.complex128, engine_factory=factory)
+        sv = DistStateVector(n, np.complex128, engine_factory=factory, swap=swap)
         ops = mixed_circuit(n, seed)
         sv.apply_ops(ops, fuse=True)
         z = sv.expval_z_all()
@@ -121,12 +121,12 @@ def worker(rank, world, n, seed, port, backend, q):
         dist.destroy_process_group()
 
 
-def run_ranks(world, n, seed, backend="gloo", port=29611):
+def run_ranks(world, n, seed, backend="gloo", port=29611, swap="auto"):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, world, n, seed, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, n, seed, port, backend, q, swap)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=300)
