@@ -336,13 +336,26 @@ template <typename T2>
 __global__ void __launch_bounds__(kThreads)
     swap_peer_kernel(T2 *__restrict__ mine, T2 *__restrict__ peer, uint64_t lo, uint64_t hi,
                      const __grid_constant__ BitInsert ins, uint64_t my_bit, uint64_t peer_bit) {
+    // 4 independent local + 4 independent NVLink loads in flight per thread before any store
+    constexpr int U = 4;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t g = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < hi; g += stride) {
-        const uint64_t b = insert_bits(g, ins);
-        const T2 a = mine[b | my_bit];
-        const T2 c = peer[b | peer_bit];
-        mine[b | my_bit] = c;
-        peer[b | peer_bit] = a;
+    for (uint64_t g0 = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < hi; g0 += U * stride) {
+        uint64_t b[U];
+        T2 a[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t g = g0 + u * stride;
+            b[u] = insert_bits(g < hi ? g : g0, ins);
+            c[u] = peer[b[u] | peer_bit];
+            a[u] = mine[b[u] | my_bit];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (g0 + u * stride < hi) {
+                mine[b[u] | my_bit] = c[u];
+                peer[b[u] | peer_bit] = a[u];
+            }
+        }
     }
 }
 
@@ -690,7 +703,8 @@ void swap_bit_peer(StateVec &sv, int bit, int keep, void *peer, int do_half) {
     const uint64_t half = sv.length() >> 1;
     const uint64_t lo = do_half == 0 ? 0 : (do_half == 1 ? 0 : half / 2);
     const uint64_t hi = do_half == 0 ? half : (do_half == 1 ? half / 2 : half);
-    const int nb = reduce_blocks(sv, hi - lo);
+    const int nb = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((hi - lo + kThreads * 4 - 1) / (kThreads * 4),
+                                                                             uint64_t(sv.sm_count) * 32)));
     const BitInsert ins = single_insert(bit);
     const uint64_t my_bit = keep ? 0 : (uint64_t{1} << bit);
     const uint64_t peer_bit = keep ? (uint64_t{1} << bit) : 0;
