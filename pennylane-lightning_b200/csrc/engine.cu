@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -806,6 +807,54 @@ int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, i
     for (int64_t i = 0; i < n_obs; i++) {
         hl.push_back(std::make_unique<TempState>(ref, false));
         obs_apply_to(*obs[i], hl.back()->s, lambda.s);
+    }
+    // ---- single observable, every trainable generator a (controlled) Pauli word: the whole backward
+    //      sweep runs as fused two-state tile passes (fusion.cu)
+    bool fuse_ok = (n_obs == 1) && std::getenv("PLB200_ADJOINT_UNFUSED") == nullptr;
+    if (fuse_ok) {
+        std::vector<AdjItem> items;
+        std::vector<double> sfs(n_tp, 0.0);
+        int64_t tpi = n_tp - 1, cur = num_param_ops - 1;
+        for (int64_t op_idx = n_ops - 1; op_idx >= 0 && fuse_ok; op_idx--) {
+            const GateCall &c = calls[op_idx];
+            PLB_CHECK(c.params.size() <= 1,
+                      "The operation is not supported using the adjoint differentiation method");
+            if (c.name == "StatePrep" || c.name == "BasisState") continue;
+            if (tpi < 0) break;
+            if (!c.params.empty()) {
+                if (cur == tp[tpi]) {
+                    AdjItem it;
+                    it.overlap = true;
+                    double gscale = 0;
+                    if (!generator_as_pauli(ref.n, c, &it.pw, &gscale)) {
+                        fuse_ok = false;
+                        break;
+                    }
+                    it.slot = static_cast<int>(tpi);
+                    sfs[tpi] = gscale * (c.inverse ? -1.0 : 1.0);
+                    items.push_back(std::move(it));
+                    tpi--;
+                }
+                cur--;
+            }
+            if (tpi < 0) break;
+            GateCall inv = c;
+            inv.inverse = !c.inverse;
+            for (auto &lo : lower_gate(ref.n, inv)) {
+                AdjItem it;
+                it.op = std::move(lo);
+                items.push_back(std::move(it));
+            }
+        }
+        if (fuse_ok) {
+            std::vector<double> acc(n_tp, 0.0);
+            int64_t st[3];
+            run_adjoint_fused(lambda.s, hl[0]->s, items, static_cast<int>(n_tp), acc.data(), st);
+            for (int64_t p = 0; p < n_tp; p++) jac[p] = -2.0 * sfs[p] * acc[p];
+            const_cast<StateVec &>(ref).launches += lambda.s.launches + hl[0]->s.launches;
+            const_cast<StateVec &>(ref).last_stats[0] = st[0], const_cast<StateVec &>(ref).last_stats[1] = st[1];
+            return 0;
+        }
     }
     std::unique_ptr<TempState> mu; // only for generators that are not (controlled) Pauli words
 

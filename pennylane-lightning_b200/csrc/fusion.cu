@@ -1,4 +1,5 @@
-// Cache-blocked ("tile") execution of a tape of canonical ops — the gate-fusion pass.
+// Cache-blocked ("tile") execution of a tape of canonical ops — the gate-fusion pass, and its
+// two-state variant that runs the adjoint-Jacobian sweep.
 //
 // The reference sweeps the whole 2^n vector once per gate ("one full HBM
 // read+write per gate ... no fusion anywhere").  Here the tape is scheduled into PASSES: a pass
@@ -12,6 +13,12 @@
 // register pairs, phases on single registers), and stores them back.  Per-gate arithmetic is the
 // same 2x2 complex update as the un-fused kernels, so results agree to rounding.
 //
+// Adjoint variant (AdjointJacobianLQubit.hpp:269-314 as ONE sweep per block of ops): the tile of
+// lambda and the tile of H·lambda travel together; walking the tape backwards, a trainable op first
+// contributes its overlap Im<H lambda| G |lambda> (G = (controlled) X / Y / Z-parity generator)
+// from registers — accumulated per CTA in shared memory, flushed once with fp64 atomics — and then
+// its inverse is applied to both tiles.  No mu copy, no per-op HBM sweep.
+//
 // Gate commutation used by the scheduler: ops acting on disjoint bit sets commute, nothing else.
 #include "fusion.hpp"
 
@@ -22,23 +29,27 @@ namespace plb200 {
 
 namespace {
 
-#ifndef PLB_KR
-#define PLB_KR 4
-#endif
-constexpr int kR = PLB_KR; // register bits per round (2^kR amplitudes per thread)
-constexpr int kMaxRoundOps = 4096;
+constexpr int kMaxR = 4;
+constexpr int kMaxPassOps = 224;
+constexpr int kMaxPassRounds = 22;
 
-template <typename T2> struct TileCfg;
-template <> struct TileCfg<double2> {
-    static constexpr int M = 12;  // 2^12 x 16 B = 64 KiB tile
-    static constexpr int LOW = 3; // 8 x 16 B = 128 B contiguous
+// forward pass: one state, 2^12 (c128) / 2^13 (c64) amplitudes = 64 KiB per tile, 16 per thread
+template <typename T2> struct FwdCfg;
+template <> struct FwdCfg<double2> {
+    static constexpr int M = 12, LOW = 3, R = 4, NS = 1, MINB = 2;
 };
-template <> struct TileCfg<float2> {
-    static constexpr int M = 13;  // 2^13 x 8 B = 64 KiB tile
-    static constexpr int LOW = 4; // 16 x 8 B = 128 B contiguous
+template <> struct FwdCfg<float2> {
+    static constexpr int M = 13, LOW = 4, R = 4, NS = 1, MINB = 2;
+};
+// adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
+template <typename T2> struct AdjCfg;
+template <> struct AdjCfg<double2> {
+    static constexpr int M = 11, LOW = 3, R = 3, NS = 2, MINB = 2;
+};
+template <> struct AdjCfg<float2> {
+    static constexpr int M = 12, LOW = 4, R = 3, NS = 2, MINB = 2;
 };
 
-// ------------------------------------------------------------------ device-side plan layout
 // op kinds inside a tile pass
 enum : int {
     TK_GENERAL = 0, // complex 2x2 on register bit p
@@ -50,13 +61,14 @@ enum : int {
     TK_DIAG_G = 6,  // ... any register bits (per-amplitude select)
     TK_DIAG1_T = 7, // as DIAG_T with m[0] == 1: only the parity-1 amplitudes are multiplied
     TK_DIAG1_R = 8, // as DIAG_R with m[0] == 1
+    TK_OVL_X = 16,  // adjoint: accumulate Im<h| X_p |l> (controlled by the active mask)
+    TK_OVL_Y = 17,  // adjoint: Im<h| Y_p |l>
+    TK_OVL_D = 18,  // adjoint: Im<h| D |l>, D = diag(g[parity]), g = (m[0].x, m[0].y)
 };
-constexpr int kMaxPassOps = 224;
-constexpr int kMaxPassRounds = 22;
 
 // Controls / parity masks are split on the host into a per-thread part (tile-local index bits that
-// are thread bits in this round) and a per-register part (16-bit patterns over the register index
-// u), so that the per-amplitude predicate is a single bit test on a compile-time position.
+// are thread bits in this round) and a per-register part (bit patterns over the register index u),
+// so that the per-amplitude predicate is a single bit test on a compile-time position.
 template <typename T2> struct alignas(16) TileOp {
     int kind;
     int p;
@@ -64,18 +76,19 @@ template <typename T2> struct alignas(16) TileOp {
     uint32_t pm_thr;         // parity mask on thread bits
     uint32_t umask;          // bit u: register index u satisfies the register-bit controls
     uint32_t upar;           // bit u: parity of u's register bits under the parity mask
-    uint32_t pad;
+    uint32_t slot;           // adjoint: accumulator slot of this overlap inside the pass
     uint64_t cmask_o, cval_o, pmask_o; // bits outside the tile: uniform per tile
     T2 m[4];
 };
 struct alignas(16) RoundHdr {
     int first_op, nops;
-    uint32_t lowmask[kR]; // insertion masks (ascending local positions)
-    uint32_t roff[1 << kR];
+    uint32_t lowmask[kMaxR]; // insertion masks (ascending local positions)
+    uint32_t roff[1 << kMaxR];
 };
 struct alignas(16) PassHdr {
     int nrounds, nops_total;
     uint64_t ntiles;
+    int nslots, pad;
     BitInsert tile_ins; // zeros at the M tile bits
 };
 // The whole pass description travels as a __grid_constant__ kernel parameter (constant bank,
@@ -88,11 +101,11 @@ template <typename T2> struct alignas(16) PassParams {
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
 
-template <typename T2, int P, int KIND>
-__device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active) {
+template <typename T2, int R, int P, int KIND>
+__device__ __forceinline__ void apply_pair(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active) {
     const T2 m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
 #pragma unroll
-    for (int q = 0; q < (1 << (kR - 1)); q++) {
+    for (int q = 0; q < (1 << (R - 1)); q++) {
         const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
         const int u1 = u0 | (1 << P);
         if (active & (1u << u0)) {
@@ -114,59 +127,143 @@ __device__ __forceinline__ void apply_pair(T2 (&v)[1 << kR], const TileOp<T2> &o
     }
 }
 
-template <typename T2, int P, bool ONE>
-__device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << kR], const TileOp<T2> &op, uint32_t active, bool pt) {
+template <typename T2, int R, int P, bool ONE>
+__device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active, bool pt) {
     if constexpr (ONE) {
         const T2 d1 = op.m[1];
 #pragma unroll
-        for (int u = 0; u < (1 << kR); u++) {
+        for (int u = 0; u < (1 << R); u++) {
             const bool par = ((u >> P) & 1) ? !pt : pt;
             if ((active & (1u << u)) && par) v[u] = cmul(v[u], d1);
         }
     } else {
         const T2 da = pt ? op.m[1] : op.m[0], db = pt ? op.m[0] : op.m[1];
 #pragma unroll
-        for (int u = 0; u < (1 << kR); u++)
+        for (int u = 0; u < (1 << R); u++)
             if (active & (1u << u)) v[u] = cmul(v[u], ((u >> P) & 1) ? db : da);
     }
 }
 
-#define PLB_SWITCH_P(CALL)                                                                               \
+#define PLB_SWITCH_P(R, CALL)                                                                            \
     switch (op.p) {                                                                                      \
     case 0: { constexpr int P = 0; CALL; } break;                                                        \
-    case 1: { constexpr int P = 1; CALL; } break;                                                        \
-    case 2: { constexpr int P = (kR > 2 ? 2 : kR - 1); CALL; } break;                                                        \
-    default: { constexpr int P = (kR > 3 ? 3 : kR - 1); CALL; } break;                                                       \
+    case 1: { constexpr int P = (R > 1 ? 1 : 0); CALL; } break;                                          \
+    case 2: { constexpr int P = (R > 2 ? 2 : R - 1); CALL; } break;                                      \
+    default: { constexpr int P = (R > 3 ? 3 : R - 1); CALL; } break;                                     \
     }
 
-template <typename T2>
-__global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
-    tile_kernel(T2 *__restrict__ sv, const uint64_t *__restrict__ goff_g, const __grid_constant__ PassParams<T2> pp) {
-    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
-    constexpr int NT = 1 << (M - kR);
-    constexpr int NV = 1 << kR;
+// one gate op on one register set
+template <typename T2, int R>
+__device__ __forceinline__ void apply_gate(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active, bool pt) {
+    switch (op.kind) {
+    case TK_GENERAL:
+        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_GENERAL>(v, op, active)));
+        break;
+    case TK_SWAP:
+        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_SWAP>(v, op, active)));
+        break;
+    case TK_REAL:
+        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_REAL>(v, op, active)));
+        break;
+    case TK_RXLIKE:
+        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_RXLIKE>(v, op, active)));
+        break;
+    case TK_DIAG_T: {
+        const T2 d = pt ? op.m[1] : op.m[0];
+#pragma unroll
+        for (int u = 0; u < (1 << R); u++)
+            if (active & (1u << u)) v[u] = cmul(v[u], d);
+    } break;
+    case TK_DIAG1_T:
+        if (pt) {
+            const T2 d = op.m[1];
+#pragma unroll
+            for (int u = 0; u < (1 << R); u++)
+                if (active & (1u << u)) v[u] = cmul(v[u], d);
+        }
+        break;
+    case TK_DIAG_R:
+        PLB_SWITCH_P(R, (apply_diag_r<T2, R, P, false>(v, op, active, pt)));
+        break;
+    case TK_DIAG1_R:
+        PLB_SWITCH_P(R, (apply_diag_r<T2, R, P, true>(v, op, active, pt)));
+        break;
+    default: {
+        const uint32_t pb = pt ? ~op.upar : op.upar;
+        const T2 d0 = op.m[0], d1 = op.m[1];
+#pragma unroll
+        for (int u = 0; u < (1 << R); u++)
+            if (active & (1u << u)) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
+    } break;
+    }
+}
+
+// Im(conj(a) b), Re(conj(a) b)
+template <typename T2> __device__ __forceinline__ double im_cb(T2 a, T2 b) {
+    return static_cast<double>(a.x) * b.y - static_cast<double>(a.y) * b.x;
+}
+template <typename T2> __device__ __forceinline__ double re_cb(T2 a, T2 b) {
+    return static_cast<double>(a.x) * b.x + static_cast<double>(a.y) * b.y;
+}
+
+template <typename T2, int R, int P, bool ISY>
+__device__ __forceinline__ double overlap_pair(const T2 (&l)[1 << R], const T2 (&h)[1 << R], uint32_t active) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < (1 << (R - 1)); q++) {
+        const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
+        const int u1 = u0 | (1 << P);
+        if (active & (1u << u0)) {
+            // (Y l)[u0] = -i l[u1], (Y l)[u1] = i l[u0];  (X l)[u0] = l[u1], (X l)[u1] = l[u0]
+            if constexpr (ISY) s += re_cb(h[u1], l[u0]) - re_cb(h[u0], l[u1]);
+            else s += im_cb(h[u0], l[u1]) + im_cb(h[u1], l[u0]);
+        }
+    }
+    return s;
+}
+
+template <typename T2, class Cfg>
+__global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
+    tile_kernel(T2 *__restrict__ sv0, T2 *__restrict__ sv1, const uint64_t *__restrict__ goff_g,
+                double *__restrict__ acc_g, const __grid_constant__ PassParams<T2> pp) {
+    constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NS = Cfg::NS;
+    constexpr int NT = 1 << (M - R);
+    constexpr int NV = 1 << R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T2 *tile = reinterpret_cast<T2 *>(smem_raw);
-    uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(T2) << M));
+    T2 *tile0 = reinterpret_cast<T2 *>(smem_raw);
+    T2 *tile1 = tile0 + (NS == 2 ? (1 << M) : 0);
+    uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + NS * (sizeof(T2) << M));
+    double *acc = reinterpret_cast<double *>(goff + (1 << (M - LOW)));
     static_assert(sizeof(PassParams<T2>) <= 32764, "kernel parameter space");
 
     for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
+    if constexpr (NS == 2)
+        for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT) acc[i] = 0.0;
     __syncthreads();
     const uint32_t tid = threadIdx.x;
     const int nrounds = pp.hdr.nrounds;
 
     for (uint64_t t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
         const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
-        // ---- load the tile (coalesced 128-byte lines)
+        // ---- load the tile(s) (coalesced 128-byte lines)
         {
             T2 v[NV];
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 const uint32_t j = tid + u * NT;
-                v[u] = sv[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
+                v[u] = sv0[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
             }
 #pragma unroll
-            for (int u = 0; u < NV; u++) tile[swz(tid + u * NT)] = v[u];
+            for (int u = 0; u < NV; u++) tile0[swz(tid + u * NT)] = v[u];
+            if constexpr (NS == 2) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) {
+                    const uint32_t j = tid + u * NT;
+                    v[u] = sv1[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
+                }
+#pragma unroll
+                for (int u = 0; u < NV; u++) tile1[swz(tid + u * NT)] = v[u];
+            }
         }
         __syncthreads();
         // ---- rounds
@@ -174,75 +271,80 @@ __global__ void __launch_bounds__(1 << (TileCfg<T2>::M - kR))
             const RoundHdr &rh = pp.rounds[r];
             uint32_t jbase = tid;
 #pragma unroll
-            for (int i = 0; i < kR; i++) {
+            for (int i = 0; i < R; i++) {
                 const uint32_t lm = rh.lowmask[i];
                 jbase = ((jbase & ~lm) << 1) | (jbase & lm);
             }
             T2 v[NV];
+            T2 h[NS == 2 ? NV : 1];
 #pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = tile[swz(jbase | rh.roff[u])];
+            for (int u = 0; u < NV; u++) v[u] = tile0[swz(jbase | rh.roff[u])];
+            if constexpr (NS == 2) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) h[u] = tile1[swz(jbase | rh.roff[u])];
+            }
             const int k_end = rh.first_op + rh.nops;
             for (int k = rh.first_op; k < k_end; k++) {
                 const TileOp<T2> &op = pp.ops[k];
                 if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
                 const uint32_t active = ((jbase & op.cm_thr) == op.cv_thr) ? op.umask : 0u;
-                switch (op.kind) {
-                case TK_GENERAL:
-                    PLB_SWITCH_P((apply_pair<T2, P, TK_GENERAL>(v, op, active)));
-                    break;
-                case TK_SWAP:
-                    PLB_SWITCH_P((apply_pair<T2, P, TK_SWAP>(v, op, active)));
-                    break;
-                case TK_REAL:
-                    PLB_SWITCH_P((apply_pair<T2, P, TK_REAL>(v, op, active)));
-                    break;
-                case TK_RXLIKE:
-                    PLB_SWITCH_P((apply_pair<T2, P, TK_RXLIKE>(v, op, active)));
-                    break;
-                default: {
-                    const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
-                    if (op.kind == TK_DIAG_T) {
-                        const T2 d = pt ? op.m[1] : op.m[0];
-#pragma unroll
-                        for (int u = 0; u < NV; u++)
-                            if (active & (1u << u)) v[u] = cmul(v[u], d);
-                    } else if (op.kind == TK_DIAG1_T) {
-                        if (pt) {
-                            const T2 d = op.m[1];
+                const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
+                if constexpr (NS == 2) {
+                    if (op.kind >= TK_OVL_X) {
+                        double s = 0;
+                        if (op.kind == TK_OVL_X) {
+                            PLB_SWITCH_P(R, (s = overlap_pair<T2, R, P, false>(v, h, active)));
+                        } else if (op.kind == TK_OVL_Y) {
+                            PLB_SWITCH_P(R, (s = overlap_pair<T2, R, P, true>(v, h, active)));
+                        } else {
+                            const uint32_t pb = pt ? ~op.upar : op.upar;
+                            const double g0 = op.m[0].x, g1 = op.m[0].y;
 #pragma unroll
                             for (int u = 0; u < NV; u++)
-                                if (active & (1u << u)) v[u] = cmul(v[u], d);
+                                if (active & (1u << u)) s += ((pb >> u & 1) ? g1 : g0) * im_cb(h[u], v[u]);
                         }
-                    } else if (op.kind == TK_DIAG_R) {
-                        PLB_SWITCH_P((apply_diag_r<T2, P, false>(v, op, active, pt)));
-                    } else if (op.kind == TK_DIAG1_R) {
-                        PLB_SWITCH_P((apply_diag_r<T2, P, true>(v, op, active, pt)));
-                    } else {
-                        const uint32_t pb = pt ? ~op.upar : op.upar;
-                        const T2 d0 = op.m[0], d1 = op.m[1];
 #pragma unroll
-                        for (int u = 0; u < NV; u++)
-                            if (active & (1u << u)) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if ((tid & 31) == 0) atomicAdd(&acc[op.slot], s);
+                        continue;
                     }
-                } break;
+                    apply_gate<T2, R>(h, op, active, pt);
                 }
+                apply_gate<T2, R>(v, op, active, pt);
             }
 #pragma unroll
-            for (int u = 0; u < NV; u++) tile[swz(jbase | rh.roff[u])] = v[u];
+            for (int u = 0; u < NV; u++) tile0[swz(jbase | rh.roff[u])] = v[u];
+            if constexpr (NS == 2) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) tile1[swz(jbase | rh.roff[u])] = h[u];
+            }
             __syncthreads();
         }
-        // ---- store the tile
+        // ---- store the tile(s)
         {
             T2 v[NV];
 #pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = tile[swz(tid + u * NT)];
+            for (int u = 0; u < NV; u++) v[u] = tile0[swz(tid + u * NT)];
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 const uint32_t j = tid + u * NT;
-                sv[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
+                sv0[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
+            }
+            if constexpr (NS == 2) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) v[u] = tile1[swz(tid + u * NT)];
+#pragma unroll
+                for (int u = 0; u < NV; u++) {
+                    const uint32_t j = tid + u * NT;
+                    sv1[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
+                }
             }
         }
         __syncthreads();
+    }
+    if constexpr (NS == 2) {
+        for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT)
+            if (acc[i] != 0.0) atomicAdd(&acc_g[i], acc[i]);
     }
 }
 
@@ -279,6 +381,18 @@ FOp classify(const COp &op) {
         if (!op.parity && op.k() == 0 && op.cmask == 0) f.all = 0; // global scalar commutes with everything
     }
     if (!f.fusable) f.nd = t;
+    return f;
+}
+
+FOp classify(const AdjItem &it) {
+    if (!it.overlap) return classify(it.op);
+    FOp f;
+    const PauliWordMask &w = it.pw;
+    f.nd = w.x;
+    f.all = w.x | w.z | w.cmask;
+    const int nx = __builtin_popcountll(w.x);
+    // fused overlaps: Z-parity words, or a single X / Y factor (no extra Z factors)
+    f.fusable = (nx == 0) || (nx == 1 && (w.z == 0 || w.z == w.x));
     return f;
 }
 
@@ -338,29 +452,30 @@ uint64_t grow(const std::vector<FOp> &f, const std::vector<int> &pending, uint64
 }
 
 struct HostPass {
-    std::vector<int> tbits;                 // sorted ascending, size M
-    std::vector<std::vector<int>> rounds;   // op indices per round
-    std::vector<uint64_t> round_bits;       // register bits (global bit masks) per round
+    std::vector<int> tbits;               // sorted ascending, size M
+    std::vector<std::vector<int>> rounds; // item indices per round
+    std::vector<uint64_t> round_bits;     // register bits (global bit masks) per round
 };
 
 struct Step {
-    int op = -1;    // >= 0: standalone op
-    size_t off = 0; // else: offset of the pass's goff table in the arena (bytes)
+    int op = -1;       // >= 0: stand-alone item
+    size_t off = 0;    // else: offset of the pass's goff table in the arena (bytes)
     size_t params = 0; // index into the params vector
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
+    std::vector<int> slots; // adjoint: global accumulator slot of each pass-local slot
 };
 
-// Pure host: schedule `ops` on an n-qubit state into tile passes / stand-alone ops.
-template <typename T2>
-void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vector<Step> &steps,
+// Pure host: schedule `items` on an n-qubit state into tile passes / stand-alone items.
+template <typename T2, class Cfg>
+void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std::vector<Step> &steps,
                     std::vector<unsigned char> &arena, std::vector<PassParams<T2>> &params) {
-    params.clear();
-    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
+    constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R;
     steps.clear();
     arena.clear();
-    if (n < M + 1 || ops.size() < 2) {
-        for (size_t i = 0; i < ops.size(); i++) {
+    params.clear();
+    if (n < M + 1 || items.size() < 2) {
+        for (size_t i = 0; i < items.size(); i++) {
             Step st;
             st.op = static_cast<int>(i);
             steps.push_back(st);
@@ -368,28 +483,27 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
         return;
     }
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
-    std::vector<FOp> f(ops.size());
-    for (size_t i = 0; i < ops.size(); i++) {
-        f[i] = classify(ops[i]);
+    std::vector<FOp> f(items.size());
+    for (size_t i = 0; i < items.size(); i++) {
+        f[i] = classify(items[i]);
         f[i].all &= full;
     }
-    std::vector<char> done(ops.size(), 0);
+    std::vector<char> done(items.size(), 0);
     size_t first = 0;
     const size_t window = 512;
     const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
-
     std::vector<int> pending, exec;
 
     while (true) {
-        while (first < ops.size() && done[first]) first++;
-        if (first >= ops.size()) break;
+        while (first < items.size() && done[first]) first++;
+        if (first >= items.size()) break;
         pending.clear();
-        for (size_t i = first; i < ops.size() && pending.size() < window; i++)
+        for (size_t i = first; i < items.size() && pending.size() < window; i++)
             if (!done[i]) pending.push_back(static_cast<int>(i));
         // ---- choose the tile bits
         uint64_t T = grow(f, pending, lowbits, M, full, full, exec);
         if (exec.size() < 2) {
-            // nothing worth a tile pass: run the first pending op on its own
+            // nothing worth a tile pass: run the first pending item on its own
             Step st;
             st.op = static_cast<int>(first);
             steps.push_back(st);
@@ -409,12 +523,11 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
         std::vector<int> rem = pass_ops, rexec;
         while (!rem.empty()) {
             uint64_t seed = f[rem[0]].nd; // guarantees progress
-            uint64_t Rb = grow(f, rem, seed, kR, T, full, rexec);
-            // pad to kR bits with tile bits (prefer high local bits: conflict-free shared accesses)
-            for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < kR; i--) Rb |= uint64_t{1} << hp.tbits[i];
+            uint64_t Rb = grow(f, rem, seed, R, T, full, rexec);
+            // pad to R bits with tile bits (prefer high local bits: conflict-free shared accesses)
+            for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < R; i--) Rb |= uint64_t{1} << hp.tbits[i];
             simulate(f, rem, Rb, full, rexec);
             if (rexec.empty()) fail("fusion scheduler made no progress");
-            if (rexec.size() > static_cast<size_t>(kMaxRoundOps)) rexec.resize(kMaxRoundOps);
             hp.rounds.push_back(rexec);
             hp.round_bits.push_back(Rb);
             std::vector<int> next;
@@ -461,6 +574,7 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                 if (mask >> hp.tbits[i] & 1) l |= 1u << i;
             return l;
         };
+        Step st;
         int op_cursor = 0;
         for (size_t r = 0; r < hp.rounds.size(); r++) {
             std::vector<int> rl; // local positions of the register bits, ascending
@@ -468,40 +582,56 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                 if (hp.round_bits[r] >> hp.tbits[i] & 1) rl.push_back(i);
             rh[r].first_op = op_cursor;
             rh[r].nops = static_cast<int>(hp.rounds[r].size());
-            for (int i = 0; i < kR; i++) rh[r].lowmask[i] = (1u << rl[i]) - 1;
-            for (int u = 0; u < (1 << kR); u++) {
+            for (int i = 0; i < R; i++) rh[r].lowmask[i] = (1u << rl[i]) - 1;
+            for (int u = 0; u < (1 << R); u++) {
                 uint32_t o = 0;
-                for (int i = 0; i < kR; i++)
+                for (int i = 0; i < R; i++)
                     if (u >> i & 1) o |= 1u << rl[i];
                 rh[r].roff[u] = o;
             }
+            uint32_t rmask_l = 0;
+            for (int i = 0; i < R; i++) rmask_l |= 1u << rl[i];
             for (int idx : hp.rounds[r]) {
-                const COp &op = ops[idx];
+                const AdjItem &it = items[idx];
                 const FOp &fo = f[idx];
                 TileOp<T2> &t = top[op_cursor++];
-                const uint32_t cm_l = to_local(op.cmask & T), cv_l = to_local(op.cval & T);
-                uint32_t rmask_l = 0;
-                for (int i = 0; i < kR; i++) rmask_l |= 1u << rl[i];
+                const uint64_t cmask = it.overlap ? it.pw.cmask : it.op.cmask;
+                const uint64_t cval = it.overlap ? it.pw.cval : it.op.cval;
+                const uint64_t pmask = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : fo.pmask);
+                const uint32_t cm_l = to_local(cmask & T), cv_l = to_local(cval & T), pm_l = to_local(pmask & T);
                 t.cm_thr = cm_l & ~rmask_l, t.cv_thr = cv_l & ~rmask_l;
-                t.cmask_o = op.cmask & ~T, t.cval_o = op.cval & ~T;
-                const uint32_t pm_l = (op.kind == OP_PAIRS) ? 0u : to_local(fo.pmask & T);
+                t.cmask_o = cmask & ~T, t.cval_o = cval & ~T;
                 t.pm_thr = pm_l & ~rmask_l;
+                t.pmask_o = pmask & ~T;
                 t.umask = 0, t.upar = 0;
-                for (int u = 0; u < (1 << kR); u++) {
+                for (int u = 0; u < (1 << R); u++) {
                     const uint32_t ro = rh[r].roff[u];
                     if ((ro & cm_l) == (cv_l & rmask_l)) t.umask |= 1u << u;
                     if (__builtin_popcount(ro & pm_l) & 1) t.upar |= 1u << u;
                 }
-                if (op.kind == OP_PAIRS) {
-                    const cd *m = op.blocks[0].m;
+                auto reg_pos = [&](int global_bit) {
+                    const int lp = local_of[global_bit];
+                    return static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
+                };
+                if (it.overlap) {
+                    t.slot = static_cast<uint32_t>(st.slots.size());
+                    st.slots.push_back(it.slot);
+                    if (it.pw.x) {
+                        t.kind = (it.pw.z == it.pw.x) ? TK_OVL_Y : TK_OVL_X;
+                        t.p = reg_pos(__builtin_ctzll(it.pw.x));
+                    } else {
+                        t.kind = TK_OVL_D;
+                        t.m[0] = mk<T2>(1.0, it.pw.z ? -1.0 : 1.0);
+                    }
+                } else if (it.op.kind == OP_PAIRS) {
+                    const cd *m = it.op.blocks[0].m;
                     t.kind = TK_GENERAL;
                     if (m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0)) t.kind = TK_SWAP;
                     else if (m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0)
                         t.kind = TK_REAL;
                     else if (m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0)
                         t.kind = TK_RXLIKE;
-                    const int lp = local_of[op.tbits[0]];
-                    t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
+                    t.p = reg_pos(it.op.tbits[0]);
                     for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(m[q].real(), m[q].imag());
                 } else {
                     const bool one = (fo.d[0] == cd(1.0));
@@ -513,39 +643,51 @@ void build_schedule(int n, int sm_count, const std::vector<COp> &ops, std::vecto
                         t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
                     } else
                         t.kind = TK_DIAG_G;
-                    t.pmask_o = fo.pmask & ~T;
                     t.m[0] = mk<T2>(fo.d[0].real(), fo.d[0].imag());
                     t.m[1] = mk<T2>(fo.d[1].real(), fo.d[1].imag());
                 }
             }
         }
-        Step st;
+        hdr->nslots = static_cast<int>(st.slots.size());
         st.off = off;
         st.params = params.size() - 1;
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
         st.nrounds = hdr->nrounds, st.nops = hdr->nops_total;
-        steps.push_back(st);
+        steps.push_back(std::move(st));
     }
 }
 
+template <class Cfg, typename T2> size_t smem_bytes_for() {
+    return Cfg::NS * (sizeof(T2) << Cfg::M) + (sizeof(uint64_t) << (Cfg::M - Cfg::LOW)) +
+           (Cfg::NS == 2 ? sizeof(double) * kMaxPassOps : 0);
+}
+
+template <typename T2, class Cfg> void prepare_kernel() {
+    static bool done = false;
+    if (done) return;
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes_for<Cfg, T2>())));
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    done = true;
+}
+
+std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
+    std::vector<AdjItem> items(ops.size());
+    for (size_t i = 0; i < ops.size(); i++) items[i].op = ops[i];
+    return items;
+}
+
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
-    constexpr int M = TileCfg<T2>::M, LOW = TileCfg<T2>::LOW;
+    using Cfg = FwdCfg<T2>;
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
     std::vector<PassParams<T2>> params;
-    build_schedule<T2>(static_cast<int>(sv.n), sv.sm_count, ops, steps, arena, params);
-    auto smem_bytes = (sizeof(T2) << M) + (sizeof(uint64_t) << (M - LOW));
-    static bool attr_set_d = false, attr_set_f = false;
-    bool &attr_set = sizeof(T2) == 16 ? attr_set_d : attr_set_f;
-    if (!attr_set && !arena.empty()) {
-        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem_bytes)));
-        PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
-    }
-    // ---- upload every pass plan once, then launch the whole schedule back to back
+    const auto items = as_items(ops);
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, steps, arena, params);
+    // ---- upload every pass's offset table once, then launch the whole schedule back to back
     unsigned char *dplan = nullptr;
     if (!arena.empty()) {
+        prepare_kernel<T2, Cfg>();
         dplan = static_cast<unsigned char *>(sv.plan_buf(arena.size()));
         PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, sv.stream));
         PLB_CUDA(cudaStreamSynchronize(sv.stream)); // arena is a local
@@ -555,11 +697,75 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
             launch_op(sv, ops[st.op]);
             continue;
         }
-        tile_kernel<T2><<<st.grid, 1 << (M - kR), smem_bytes, sv.stream>>>(
-            static_cast<T2 *>(sv.data), reinterpret_cast<const uint64_t *>(dplan + st.off), params[st.params]);
+        tile_kernel<T2, Cfg><<<st.grid, 1 << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream>>>(
+            static_cast<T2 *>(sv.data), nullptr, reinterpret_cast<const uint64_t *>(dplan + st.off), nullptr,
+            params[st.params]);
         PLB_CUDA(cudaGetLastError());
         sv.launches++;
     }
+}
+
+template <typename T2>
+void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
+                       double *acc_host, int64_t stats[3]) {
+    using Cfg = AdjCfg<T2>;
+    std::vector<Step> steps;
+    std::vector<unsigned char> arena;
+    std::vector<PassParams<T2>> params;
+    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, steps, arena, params);
+    for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
+    // device accumulators: one slab of kMaxPassOps doubles per tile pass
+    size_t n_pass = 0;
+    for (const Step &st : steps)
+        if (st.op < 0) n_pass++;
+    unsigned char *dplan = nullptr;
+    double *dacc = nullptr;
+    const size_t acc_off = (arena.size() + 255) & ~size_t{255};
+    const size_t acc_bytes = n_pass * kMaxPassOps * sizeof(double);
+    if (n_pass) {
+        prepare_kernel<T2, Cfg>();
+        dplan = static_cast<unsigned char *>(lambda.plan_buf(acc_off + acc_bytes));
+        PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, lambda.stream));
+        dacc = reinterpret_cast<double *>(dplan + acc_off);
+        PLB_CUDA(cudaMemsetAsync(dacc, 0, acc_bytes, lambda.stream));
+        PLB_CUDA(cudaStreamSynchronize(lambda.stream));
+    }
+    size_t pass_idx = 0;
+    for (const Step &st : steps) {
+        if (st.op >= 0) {
+            const AdjItem &it = items[st.op];
+            if (it.overlap) {
+                double r[2];
+                pauli_inner(hl, lambda, &it.pw, 1, r);
+                acc_host[it.slot] += r[1];
+            } else {
+                launch_op(lambda, it.op);
+                launch_op(hl, it.op);
+            }
+            stats[1]++;
+            continue;
+        }
+        tile_kernel<T2, Cfg><<<st.grid, 1 << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), lambda.stream>>>(
+            static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data),
+            reinterpret_cast<const uint64_t *>(dplan + st.off), dacc + pass_idx * kMaxPassOps, params[st.params]);
+        PLB_CUDA(cudaGetLastError());
+        lambda.launches++;
+        pass_idx++;
+        stats[0]++;
+        stats[2] += st.nops;
+    }
+    if (n_pass) {
+        std::vector<double> h(n_pass * kMaxPassOps);
+        PLB_CUDA(cudaMemcpyAsync(h.data(), dacc, acc_bytes, cudaMemcpyDeviceToHost, lambda.stream));
+        PLB_CUDA(cudaStreamSynchronize(lambda.stream));
+        pass_idx = 0;
+        for (const Step &st : steps) {
+            if (st.op >= 0) continue;
+            for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += h[pass_idx * kMaxPassOps + s];
+            pass_idx++;
+        }
+    } else
+        lambda.sync();
 }
 
 } // namespace
@@ -567,12 +773,13 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
+    const auto items = as_items(ops);
     if (precision == 64) {
         std::vector<PassParams<double2>> params;
-        build_schedule<double2>(n, 148, ops, steps, arena, params);
+        build_schedule<double2, FwdCfg<double2>>(n, 148, items, steps, arena, params);
     } else {
         std::vector<PassParams<float2>> params;
-        build_schedule<float2>(n, 148, ops, steps, arena, params);
+        build_schedule<float2, FwdCfg<float2>>(n, 148, items, steps, arena, params);
     }
     out[0] = out[1] = out[2] = out[3] = 0;
     for (const auto &s : steps) {
@@ -585,6 +792,14 @@ void run_fused(StateVec &sv, const std::vector<COp> &ops) {
     sv.set_device();
     if (sv.precision == 64) run_fused_typed<double2>(sv, ops);
     else run_fused_typed<float2>(sv, ops);
+}
+
+void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
+                       double *acc_host, int64_t stats[3]) {
+    lambda.set_device();
+    stats[0] = stats[1] = stats[2] = 0;
+    if (lambda.precision == 64) run_adjoint_typed<double2>(lambda, hl, items, n_slots, acc_host, stats);
+    else run_adjoint_typed<float2>(lambda, hl, items, n_slots, acc_host, stats);
 }
 
 } // namespace plb200

@@ -10,4 +10,17 @@ namespace plb200 {
 void run_fused(StateVec &sv, const std::vector<COp> &ops);
 // Host-only: out = {tile passes, stand-alone kernels, rounds, ops executed inside tile passes}
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]);
+
+// One step of the backward adjoint sweep: either "apply this (already inverted) op to lambda and
+// H lambda" or "accumulate Im<H lambda| P |lambda> into slot" for a (controlled) Pauli word P.
+struct AdjItem {
+    bool overlap = false;
+    COp op;
+    PauliWordMask pw;
+    int slot = -1;
+};
+// Runs the items in order on the pair (lambda, H lambda) with tile passes over both states;
+// acc_host[slot] receives Im<H lambda|P|lambda>.  stats = {tile passes, stand-alone items, fused items}.
+void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
+                       double *acc_host, int64_t stats[3]);
 } // namespace plb200

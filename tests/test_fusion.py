@@ -88,3 +88,45 @@ def test_size_independent_properties_large(plb):
     head = sv.get_state(16)
     assert abs(head[0] - 1.0) < 1e-12 and np.max(np.abs(head[1:])) < 1e-12
     assert abs(sv.norm2() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_fused_adjoint_matches_reference(plb, ref, dtype):
+    """Single-observable adjoint runs as two-state tile passes: every fusable generator kind (X, Y,
+    Z-parity, controlled, projector), interleaved with ops/generators that must run stand-alone."""
+    n = 15
+    rng = np.random.default_rng(21)
+    ops = []
+    for layer in range(3):
+        for w in range(n):
+            g = ("RX", "RY", "RZ", "PhaseShift")[int(rng.integers(4))]
+            ops.append(circuits.op(g, [w], [rng.uniform(0, 6)], inverse=bool(rng.integers(2))))
+        perm = [int(x) for x in rng.permutation(n)]
+        for i in range(0, n - 1, 2):
+            g = ("CNOT", "CRX", "CRY", "CRZ", "ControlledPhaseShift", "IsingZZ", "IsingXX", "CZ", "SWAP",
+                 "SingleExcitation")[int(rng.integers(10))]
+            npar = 0 if g in ("CNOT", "CZ", "SWAP") else 1
+            ops.append(circuits.op(g, perm[i:i + 2], rng.uniform(0, 6, npar), inverse=bool(rng.integers(2))))
+        p = [int(x) for x in rng.permutation(n)]
+        ops.append(circuits.op("MultiRZ", p[:3], [rng.uniform(0, 6)]))
+        ops.append(circuits.op("RY", p[3:4], [rng.uniform(0, 6)], ctrl_wires=p[4:6], ctrl_values=[True, False]))
+        ops.append(circuits.op("GlobalPhase", [0], [rng.uniform(0, 6)], ctrl_wires=p[6:7], ctrl_values=[True]))
+        ops.append(circuits.op("Hadamard", p[7:8]))
+    n_par = sum(1 for o in ops if o["params"])
+    tp = sorted(int(x) for x in rng.choice(n_par, size=n_par - 7, replace=False))
+    co, words, wires = circuits.pauli_hamiltonian(n, 12, 5)
+    a, b = plb.StateVector(n, dtype), ref.StateVector(n, dtype)
+    ham_a = circuits.hamiltonian_observable(plb, co, words, wires)
+    ham_b = circuits.hamiltonian_observable(ref, co, words, wires, dtype=dtype)
+    ja = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
+    jb = b.adjoint_jacobian([ham_b], ops, tp, apply_ops=True)
+    tol = 1e-11 if dtype == np.complex128 else 2e-4
+    np.testing.assert_allclose(ja, jb, rtol=0, atol=tol)
+    # the un-fused sweep (env switch) gives the same numbers
+    import os
+    os.environ["PLB200_ADJOINT_UNFUSED"] = "1"
+    try:
+        ju = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
+    finally:
+        del os.environ["PLB200_ADJOINT_UNFUSED"]
+    np.testing.assert_allclose(ja, ju, rtol=0, atol=tol)
