@@ -307,6 +307,20 @@ class StateVector:
     def var(self, obs):
         return self._scalar("var_obs", obs._h)
 
+    def expval_shots(self, obs, shots, seed, shot_range=()):
+        r, rp = _i64(shot_range)
+        return self._scalar("expval_shots", obs._h, C.c_int64(shots), C.c_int64(seed), rp, C.c_int64(len(r)))
+
+    def var_shots(self, obs, shots, seed):
+        return self._scalar("var_shots", obs._h, C.c_int64(shots), C.c_int64(seed))
+
+    def probs_shots(self, wires, shots, seed):
+        w, wp = _i64(wires)
+        out = np.empty(1 << len(w), dtype=np.float64)
+        _check(self._f("probs_shots")(self._h, wp, C.c_int64(len(w)), C.c_int64(shots), C.c_int64(seed),
+                                      out.ctypes.data_as(_f64p)))
+        return out
+
     def generate_samples(self, shots, wires=None, seed=-1):
         if wires is None:
             nw, wp, k = -1, None, self.num_qubits

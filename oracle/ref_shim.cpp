@@ -303,6 +303,33 @@ template <class T> OpsData<SV<T>> make_ops(const OpsBlob &b) {
         for (std::size_t i = 0; i < s.size(); i++) out[i] = s[i];              \
         LQ_CATCH                                                               \
     }                                                                          \
+    /* ---------------- shot-based API (MeasurementsBase.hpp:159-521) ---- */  \
+    int lqref_expval_shots_##SFX(void *h, void *o, int64_t shots,              \
+                                 int64_t seed, const int64_t *range,           \
+                                 int64_t n_range, double *out) {               \
+        LQ_TRY Measurements<SV<T>> m(*static_cast<SV<T> *>(h));                \
+        m.setSeed(static_cast<std::size_t>(seed));                             \
+        *out = m.expval(**static_cast<Obs<T> *>(o),                            \
+                        static_cast<std::size_t>(shots),                       \
+                        vec_sz(range, n_range));                               \
+        LQ_CATCH                                                               \
+    }                                                                          \
+    int lqref_var_shots_##SFX(void *h, void *o, int64_t shots, int64_t seed,   \
+                              double *out) {                                   \
+        LQ_TRY Measurements<SV<T>> m(*static_cast<SV<T> *>(h));                \
+        m.setSeed(static_cast<std::size_t>(seed));                             \
+        *out = m.var(**static_cast<Obs<T> *>(o),                               \
+                     static_cast<std::size_t>(shots));                         \
+        LQ_CATCH                                                               \
+    }                                                                          \
+    int lqref_probs_shots_##SFX(void *h, const int64_t *w, int64_t nw,         \
+                                int64_t shots, int64_t seed, double *out) {    \
+        LQ_TRY Measurements<SV<T>> m(*static_cast<SV<T> *>(h));                \
+        m.setSeed(static_cast<std::size_t>(seed));                             \
+        auto p = m.probs(vec_sz(w, nw), static_cast<std::size_t>(shots));      \
+        for (std::size_t i = 0; i < p.size(); i++) out[i] = p[i];              \
+        LQ_CATCH                                                               \
+    }                                                                          \
     /* ---------------- adjoint Jacobian ---------------- */                   \
     int lqref_apply_ops_##SFX(void *h, const OpsBlob *blob) {                  \
         LQ_TRY auto *sv = static_cast<SV<T> *>(h);                             \

@@ -2,6 +2,8 @@
 // (Observable, NamedObsBase, HermitianObsBase, TensorProdObsBase, HamiltonianBase) and the LGPU
 // finals in lightning_gpu/observables/ObservablesGPU.hpp.  Each object owns a plb200_obs tree.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <complex>
 #include <memory>
 #include <sstream>
@@ -23,6 +25,10 @@ template <class StateVectorT> class Observable {
 
     // Apply the observable to the given state vector in place (Observables.hpp:63)
     virtual void applyInPlace(StateVectorT &sv) const { PLB200_ABI(plb200_obs_apply(h_, sv.handle())); }
+    // Rotate `sv` into the eigenbasis of the observable and report eigenvalues / wires for
+    // shot-based measurement (Observables.hpp:63-78,172-202,414-448).
+    virtual void applyInPlaceShots(StateVectorT &sv, std::vector<std::vector<PrecisionT>> &eigenValues,
+                                   std::vector<std::size_t> &ob_wires) const = 0;
     [[nodiscard]] virtual auto getObsName() const -> std::string = 0;
     [[nodiscard]] virtual auto getWires() const -> std::vector<std::size_t> = 0;
     [[nodiscard]] virtual auto getObs() const -> std::vector<std::shared_ptr<Observable<StateVectorT>>> { return {}; }
@@ -57,6 +63,25 @@ template <class StateVectorT> class NamedObs final : public Observable<StateVect
         return s.str();
     }
     [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
+    void applyInPlaceShots(StateVectorT &sv, std::vector<std::vector<PrecisionT>> &eigenValues,
+                           std::vector<std::size_t> &ob_wires) const override {
+        ob_wires.clear();
+        eigenValues.clear();
+        ob_wires.push_back(wires_[0]);
+        if (obs_name_ == "PauliX") {
+            sv.applyOperation("Hadamard", wires_, false);
+        } else if (obs_name_ == "PauliY") {
+            sv.applyOperations({"PauliZ", "S", "Hadamard"}, {wires_, wires_, wires_}, {false, false, false});
+        } else if (obs_name_ == "Hadamard") {
+            const PrecisionT theta = -M_PI / 4.0;
+            sv.applyOperation("RY", wires_, false, {theta});
+        } else if (obs_name_ == "PauliZ" || obs_name_ == "Identity") {
+        } else {
+            PLB200_ABORT("Provided NamedObs does not support shot measurement.");
+        }
+        if (obs_name_ == "Identity") eigenValues.push_back({1, 1});
+        else eigenValues.push_back({1, -1});
+    }
 
   private:
     [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
@@ -82,6 +107,12 @@ template <class StateVectorT> class HermitianObs final : public Observable<State
     }
     [[nodiscard]] auto getMatrix() const -> const MatrixT & { return matrix_; }
     [[nodiscard]] auto getObsName() const -> std::string override { return "Hermitian"; }
+    void applyInPlaceShots(StateVectorT &, std::vector<std::vector<PrecisionT>> &,
+                           std::vector<std::size_t> &) const override {
+        // the reference diagonalises with LAPACK zheev loaded at run time from scipy-openblas
+        // (Observables.hpp:236-262); SURVEY.md section 8(f) lists this as next-tier.
+        PLB200_ABORT("Hermitian observables do not support shot measurement in the B200 backend yet.");
+    }
     [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
 
   private:
@@ -109,6 +140,22 @@ template <class StateVectorT> class TensorProdObs final : public Observable<Stat
         return std::make_shared<TensorProdObs>(std::vector<ObsPtr>(obs));
     }
     [[nodiscard]] auto getSize() const -> std::size_t { return obs_.size(); }
+    void applyInPlaceShots(StateVectorT &sv, std::vector<std::vector<typename StateVectorT::PrecisionT>> &eigenValues,
+                           std::vector<std::size_t> &ob_wires) const override {
+        for (const auto &ob : obs_)
+            if (ob->getObsName().find("Hamiltonian") != std::string::npos)
+                PLB200_ABORT("Hamiltonian observables as a term of an TensorProd observable do not support shot "
+                             "measurement.");
+        eigenValues.clear();
+        ob_wires.clear();
+        for (const auto &ob : obs_) {
+            std::vector<std::vector<typename StateVectorT::PrecisionT>> ev;
+            std::vector<std::size_t> w;
+            ob->applyInPlaceShots(sv, ev, w);
+            ob_wires.push_back(w[0]);
+            eigenValues.push_back(ev[0]);
+        }
+    }
     [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return all_wires_; }
     [[nodiscard]] auto getObs() const -> std::vector<ObsPtr> override { return obs_; }
     [[nodiscard]] auto getObsName() const -> std::string override {
@@ -154,6 +201,10 @@ template <class StateVectorT> class Hamiltonian final : public Observable<StateV
     }
     [[nodiscard]] auto getObs() const -> std::vector<ObsPtr> override { return obs_; }
     [[nodiscard]] auto getCoeffs() const -> std::vector<PrecisionT> override { return coeffs_; }
+    void applyInPlaceShots(StateVectorT &, std::vector<std::vector<PrecisionT>> &,
+                           std::vector<std::size_t> &) const override {
+        PLB200_ABORT("Hamiltonian observables as a term of an observable do not support shot measurement.");
+    }
     [[nodiscard]] auto getObsName() const -> std::string override {
         std::ostringstream s;
         s << "Hamiltonian: { 'coeffs' : [";

@@ -213,6 +213,21 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
                           const py::array_t<PrecisionT, py::array::c_style | py::array::forcecast> &coeffs) {
             return mm.expval(words, wires, std::vector<PrecisionT>(coeffs.data(), coeffs.data() + coeffs.size()));
         })
+        // shot-based C++ API of MeasurementsBase (not bound by the reference; exposed for the parity tests)
+        .def("expval_shots", [](M &mm, const ObsPtr &o, std::size_t shots, const std::vector<std::size_t> &range) {
+            return mm.expval(*o, shots, range);
+        }, py::arg("obs"), py::arg("num_shots"), py::arg("shot_range") = std::vector<std::size_t>{})
+        .def("var_shots", [](M &mm, const ObsPtr &o, std::size_t shots) { return mm.var(*o, shots); })
+        .def("probs_shots", [](M &mm, const std::vector<std::size_t> &wires, std::size_t shots) {
+            return py::array_t<PrecisionT>(py::cast(mm.probs(wires, shots)));
+        })
+        .def("probs_shots", [](M &mm, const ObsPtr &o, std::size_t shots) {
+            return py::array_t<PrecisionT>(py::cast(mm.probs(*o, shots)));
+        })
+        .def("sample_obs", [](M &mm, const ObsPtr &o, std::size_t shots) {
+            return py::array_t<PrecisionT>(py::cast(mm.sample(*o, shots)));
+        })
+        .def("counts", [](M &mm, std::size_t shots) { return mm.counts(shots); })
         .def("generate_samples", [](M &mm, std::size_t num_wires, std::size_t num_shots) {
             auto s = mm.generate_samples(num_shots);
             py::array_t<std::size_t> out({num_shots, num_wires});
