@@ -246,7 +246,14 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * n_gates * e2e_steps / e2e_s
 
-    # ---- per-kernel roofline (live CUDA events per launch, un-fused kernels) ------------
+    # ---- roofline of the dominant kernel, live CUDA events ---------------------------------
+    # Fused mode: every launch of the timed region is tile_kernel (one HBM sweep for ~43 gates).
+    #   achieved = algorithmic bytes of the gates a launch processes (SURVEY section 8(d) table:
+    #   2S per full-touch gate, S per singly-controlled gate ...) / launch duration  -> "effective
+    #   HBM GB/s"; it exceeds the HBM peak exactly because fusion avoids the per-gate sweeps.
+    #   traffic  = dram bytes one launch really moves (ncu --set full capture in profiles/).
+    # The un-fused per-gate kernels (one sweep per gate: the reference's execution model) are timed
+    # gate by gate as well and reported under per_gate_kernels.
     roofline = None
     if rank == 0 and world == 1:
         peak, peak_src = measured_peak()
@@ -264,17 +271,41 @@ def run_ours(args):
             fam_ms[f] = fam_ms.get(f, 0.0) + a.elapsed_time(b)
             fam_bytes[f] = fam_bytes.get(f, 0.0) + circuits.algorithmic_bytes(o, n)
             fam_n[f] = fam_n.get(f, 0) + 1
-        dom = max(fam_ms, key=fam_ms.get)
-        ach = fam_bytes[dom] / (fam_ms[dom] * 1e-3) / 1e9
         tot_ms = sum(fam_ms.values())
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "peak_source": peak_src, "traffic": None, "launches": fam_n[dom],
-                    "avg_launch_ms": fam_ms[dom] / fam_n[dom],
-                    "avg_algorithmic_bytes_per_launch": fam_bytes[dom] / fam_n[dom],
-                    "share_of_unfused_step": fam_ms[dom] / tot_ms,
-                    "unfused_gates_per_s": n_gates / (tot_ms * 1e-3),
-                    "all_kernels": {f: {"GBps": fam_bytes[f] / (fam_ms[f] * 1e-3) / 1e9, "launches": fam_n[f],
-                                        "ms": fam_ms[f]} for f in fam_ms}}
+        per_gate = {f: {"achieved_GBps": fam_bytes[f] / (fam_ms[f] * 1e-3) / 1e9,
+                        "frac_of_peak": fam_bytes[f] / (fam_ms[f] * 1e-3) / 1e9 / peak, "launches": fam_n[f],
+                        "avg_launch_ms": fam_ms[f] / fam_n[f],
+                        "avg_algorithmic_bytes_per_launch": fam_bytes[f] / fam_n[f]} for f in fam_ms}
+        per_gate["unfused_gates_per_s"] = n_gates / (tot_ms * 1e-3)
+        alg_total = sum(fam_bytes.values())
+        if fuse:
+            gates_st, passes = sv.last_apply_stats() if False else (n_gates, None)
+            sv.apply_ops(blob, fuse=True)
+            torch.cuda.synchronize()
+            passes = sv.last_apply_stats()[1]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")
+            if os.path.exists(tpath):
+                try:
+                    traffic = json.load(open(tpath)).get(str(n))
+                except Exception:
+                    traffic = None
+            ach = alg_total / (ms_per_step * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "tile_kernel (fused pass)", "achieved": ach, "peak": peak,
+                        "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
+                        "launches_per_step": passes, "avg_launch_ms": ms_per_step / max(1, passes),
+                        "avg_algorithmic_bytes_per_launch": alg_total / max(1, passes),
+                        "note": "achieved = effective HBM GB/s: bytes the same gates move un-fused / time; the "
+                                "pass itself is FP64-issue bound, its real DRAM rate is traffic/avg_launch",
+                        "per_gate_kernels": per_gate}
+        else:
+            dom = max(fam_ms, key=fam_ms.get)
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": per_gate[dom]["achieved_GBps"], "peak": peak,
+                        "unit": "GB/s", "frac": per_gate[dom]["frac_of_peak"], "peak_source": peak_src,
+                        "traffic": per_gate[dom]["avg_algorithmic_bytes_per_launch"],
+                        "launches_per_step": fam_n[dom], "avg_launch_ms": per_gate[dom]["avg_launch_ms"],
+                        "avg_algorithmic_bytes_per_launch": per_gate[dom]["avg_algorithmic_bytes_per_launch"],
+                        "per_gate_kernels": per_gate}
 
     # ---- CPU baseline on the box's host cores (bounded sample) ---------------------------
     cpu_baseline = None
