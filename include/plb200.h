@@ -124,6 +124,11 @@ int plb200_sv_apply_pauli_rot(plb200_sv *sv, const int64_t *wires, int64_t n_wir
 int plb200_sv_apply_generator(plb200_sv *sv, const char *name, const int64_t *ctrl_wires,
                               const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires,
                               int64_t n_wires, int adj, double *scale);
+/* host-only validation of one gate call against an n-qubit state (same checks and messages as
+ * plb200_sv_apply, no device work): lets a caller queue gates lazily and still fail at call time. */
+int plb200_validate_op(int64_t num_qubits, const char *name, const int64_t *ctrl_wires,
+                       const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires, int64_t n_wires,
+                       int inverse, const double *params, int64_t n_params);
 /* applyOperations over a whole tape; `fuse` != 0 lets the engine schedule the tape into
  * cache-blocked passes (same arithmetic per gate, fewer HBM sweeps). */
 int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse);

@@ -527,6 +527,12 @@ int plb200_sv_apply(plb200_sv *sv, const char *name, const int64_t *cw, const ui
     apply_call(sv->s, make_call(name, cw, cv, nc, w, nw, inverse, params, np));
     ABI_CATCH
 }
+int plb200_validate_op(int64_t n, const char *name, const int64_t *cw, const uint8_t *cv, int64_t nc, const int64_t *w,
+                       int64_t nw, int inverse, const double *params, int64_t np) {
+    ABI_TRY
+    (void)lower_gate(n, make_call(name, cw, cv, nc, w, nw, inverse, params, np));
+    ABI_CATCH
+}
 int plb200_sv_apply_matrix(plb200_sv *sv, const double *matrix, const int64_t *cw, const uint8_t *cv, int64_t nc,
                            const int64_t *w, int64_t nw, int inverse) {
     ABI_TRY
@@ -813,39 +819,8 @@ int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, i
     bool fuse_ok = (n_obs == 1) && std::getenv("PLB200_ADJOINT_UNFUSED") == nullptr;
     if (fuse_ok) {
         std::vector<AdjItem> items;
-        std::vector<double> sfs(n_tp, 0.0);
-        int64_t tpi = n_tp - 1, cur = num_param_ops - 1;
-        for (int64_t op_idx = n_ops - 1; op_idx >= 0 && fuse_ok; op_idx--) {
-            const GateCall &c = calls[op_idx];
-            PLB_CHECK(c.params.size() <= 1,
-                      "The operation is not supported using the adjoint differentiation method");
-            if (c.name == "StatePrep" || c.name == "BasisState") continue;
-            if (tpi < 0) break;
-            if (!c.params.empty()) {
-                if (cur == tp[tpi]) {
-                    AdjItem it;
-                    it.overlap = true;
-                    double gscale = 0;
-                    if (!generator_as_pauli(ref.n, c, &it.pw, &gscale)) {
-                        fuse_ok = false;
-                        break;
-                    }
-                    it.slot = static_cast<int>(tpi);
-                    sfs[tpi] = gscale * (c.inverse ? -1.0 : 1.0);
-                    items.push_back(std::move(it));
-                    tpi--;
-                }
-                cur--;
-            }
-            if (tpi < 0) break;
-            GateCall inv = c;
-            inv.inverse = !c.inverse;
-            for (auto &lo : lower_gate(ref.n, inv)) {
-                AdjItem it;
-                it.op = std::move(lo);
-                items.push_back(std::move(it));
-            }
-        }
+        std::vector<double> sfs;
+        fuse_ok = build_adjoint_items(ref.n, calls, tp, num_param_ops, items, sfs);
         if (fuse_ok) {
             std::vector<double> acc(n_tp, 0.0);
             int64_t st[3];

@@ -8,10 +8,7 @@
 // target bits lie in T — controls and diagonal factors may sit on any bit, since outside T they
 // are uniform per tile.  One CTA loads a tile of 2^M amplitudes into shared memory, runs the
 // pass's ROUNDS on it and writes it back: ONE HBM read+write for the whole group of gates.
-// Inside the tile a round picks R "register bits": each thread pulls the 2^R amplitudes that
-// differ in those bits into registers, applies all of the round's ops there (2x2 updates on
-// register pairs, phases on single registers), and stores them back.  Per-gate arithmetic is the
-// same 2x2 complex update as the un-fused kernels, so results agree to rounding.
+// Inside the tile a round picks R "register bits"; what a thread does with them is tile_exec.cuh.
 //
 // Adjoint variant (AdjointJacobianLQubit.hpp:269-314 as ONE sweep per block of ops): the tile of
 // lambda and the tile of H·lambda travel together; walking the tape backwards, a trainable op first
@@ -23,215 +20,40 @@
 #include "fusion.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+
+#include "tile_exec.cuh"
 
 namespace plb200 {
 
 namespace {
 
-constexpr int kMaxR = 4;
-constexpr int kMaxPassOps = 224;
-constexpr int kMaxPassRounds = 22;
+using namespace tile;
 
-// forward pass: one state, 2^12 (c128) / 2^13 (c64) amplitudes = 64 KiB per tile, 16 per thread
-template <typename T2> struct FwdCfg;
-template <> struct FwdCfg<double2> {
-    static constexpr int M = 12, LOW = 3, R = 4, NS = 1, MINB = 2;
-};
-template <> struct FwdCfg<float2> {
-    static constexpr int M = 13, LOW = 4, R = 4, NS = 1, MINB = 2;
-};
-// adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
-template <typename T2> struct AdjCfg;
-template <> struct AdjCfg<double2> {
-    static constexpr int M = 11, LOW = 3, R = 3, NS = 2, MINB = 2;
-};
-template <> struct AdjCfg<float2> {
-    static constexpr int M = 12, LOW = 4, R = 3, NS = 2, MINB = 2;
-};
-
-// op kinds inside a tile pass
-enum : int {
-    TK_GENERAL = 0, // complex 2x2 on register bit p
-    TK_SWAP = 1,    // [[0,1],[1,0]] (PauliX / CNOT / Toffoli): pure register exchange, no flops
-    TK_REAL = 2,    // real 2x2 (RY, Hadamard)
-    TK_RXLIKE = 3,  // real diagonal, imaginary off-diagonal (RX)
-    TK_DIAG_T = 4,  // phase m[parity], parity bits on thread / outside bits only
-    TK_DIAG_R = 5,  // ... plus exactly one register bit p
-    TK_DIAG_G = 6,  // ... any register bits (per-amplitude select)
-    TK_DIAG1_T = 7, // as DIAG_T with m[0] == 1: only the parity-1 amplitudes are multiplied
-    TK_DIAG1_R = 8, // as DIAG_R with m[0] == 1
-    TK_OVL_X = 16,  // adjoint: accumulate Im<h| X_p |l> (controlled by the active mask)
-    TK_OVL_Y = 17,  // adjoint: Im<h| Y_p |l>
-    TK_OVL_D = 18,  // adjoint: Im<h| D |l>, D = diag(g[parity]), g = (m[0].x, m[0].y)
-};
-
-// Controls / parity masks are split on the host into a per-thread part (tile-local index bits that
-// are thread bits in this round) and a per-register part (bit patterns over the register index u),
-// so that the per-amplitude predicate is a single bit test on a compile-time position.
-template <typename T2> struct alignas(16) TileOp {
-    int kind;
-    int p;
-    uint32_t cm_thr, cv_thr; // controls on thread bits (tile-local index space)
-    uint32_t pm_thr;         // parity mask on thread bits
-    uint32_t umask;          // bit u: register index u satisfies the register-bit controls
-    uint32_t upar;           // bit u: parity of u's register bits under the parity mask
-    uint32_t slot;           // adjoint: accumulator slot of this overlap inside the pass
-    uint64_t cmask_o, cval_o, pmask_o; // bits outside the tile: uniform per tile
-    T2 m[4];
-};
-struct alignas(16) RoundHdr {
-    int first_op, nops;
-    uint32_t lowmask[kMaxR]; // insertion masks (ascending local positions)
-    uint32_t roff[1 << kMaxR];
-};
-struct alignas(16) PassHdr {
-    int nrounds, nops_total;
-    uint64_t ntiles;
-    int nslots, pad;
-    BitInsert tile_ins; // zeros at the M tile bits
-};
-// The whole pass description travels as a __grid_constant__ kernel parameter (constant bank,
-// uniform loads): nothing about the ops is fetched through the LSU/L1 data path.
-template <typename T2> struct alignas(16) PassParams {
-    PassHdr hdr;
-    RoundHdr rounds[kMaxPassRounds];
-    TileOp<T2> ops[kMaxPassOps];
-};
-
-__device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u); }
-
-template <typename T2, int R, int P, int KIND>
-__device__ __forceinline__ void apply_pair(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active) {
-    const T2 m0 = op.m[0], m1 = op.m[1], m2 = op.m[2], m3 = op.m[3];
+#if !defined(PLB200_HOST_EMU)
+struct WarpReduce {
+    double *acc;
+    __host__ __device__ __forceinline__ void operator()(int slot, double s) const {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int q = 0; q < (1 << (R - 1)); q++) {
-        const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
-        const int u1 = u0 | (1 << P);
-        if (active & (1u << u0)) {
-            const T2 a = v[u0], b = v[u1];
-            if constexpr (KIND == TK_SWAP) {
-                v[u0] = b, v[u1] = a;
-            } else if constexpr (KIND == TK_REAL) {
-                v[u0].x = fma(m1.x, b.x, m0.x * a.x), v[u0].y = fma(m1.x, b.y, m0.x * a.y);
-                v[u1].x = fma(m3.x, b.x, m2.x * a.x), v[u1].y = fma(m3.x, b.y, m2.x * a.y);
-            } else if constexpr (KIND == TK_RXLIKE) {
-                // (m0.x) a + (i m1.y) b ; (i m2.y) a + (m3.x) b
-                v[u0].x = fma(-m1.y, b.y, m0.x * a.x), v[u0].y = fma(m1.y, b.x, m0.x * a.y);
-                v[u1].x = fma(-m2.y, a.y, m3.x * b.x), v[u1].y = fma(m2.y, a.x, m3.x * b.y);
-            } else {
-                v[u0] = cfma(m1, b, cmul(m0, a));
-                v[u1] = cfma(m3, b, cmul(m2, a));
-            }
-        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&acc[slot], s);
+#else
+        (void)slot, (void)s;
+#endif
     }
-}
-
-template <typename T2, int R, int P, bool ONE>
-__device__ __forceinline__ void apply_diag_r(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active, bool pt) {
-    if constexpr (ONE) {
-        const T2 d1 = op.m[1];
-#pragma unroll
-        for (int u = 0; u < (1 << R); u++) {
-            const bool par = ((u >> P) & 1) ? !pt : pt;
-            if ((active & (1u << u)) && par) v[u] = cmul(v[u], d1);
-        }
-    } else {
-        const T2 da = pt ? op.m[1] : op.m[0], db = pt ? op.m[0] : op.m[1];
-#pragma unroll
-        for (int u = 0; u < (1 << R); u++)
-            if (active & (1u << u)) v[u] = cmul(v[u], ((u >> P) & 1) ? db : da);
-    }
-}
-
-#define PLB_SWITCH_P(R, CALL)                                                                            \
-    switch (op.p) {                                                                                      \
-    case 0: { constexpr int P = 0; CALL; } break;                                                        \
-    case 1: { constexpr int P = (R > 1 ? 1 : 0); CALL; } break;                                          \
-    case 2: { constexpr int P = (R > 2 ? 2 : R - 1); CALL; } break;                                      \
-    default: { constexpr int P = (R > 3 ? 3 : R - 1); CALL; } break;                                     \
-    }
-
-// one gate op on one register set
-template <typename T2, int R>
-__device__ __forceinline__ void apply_gate(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active, bool pt) {
-    switch (op.kind) {
-    case TK_GENERAL:
-        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_GENERAL>(v, op, active)));
-        break;
-    case TK_SWAP:
-        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_SWAP>(v, op, active)));
-        break;
-    case TK_REAL:
-        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_REAL>(v, op, active)));
-        break;
-    case TK_RXLIKE:
-        PLB_SWITCH_P(R, (apply_pair<T2, R, P, TK_RXLIKE>(v, op, active)));
-        break;
-    case TK_DIAG_T: {
-        const T2 d = pt ? op.m[1] : op.m[0];
-#pragma unroll
-        for (int u = 0; u < (1 << R); u++)
-            if (active & (1u << u)) v[u] = cmul(v[u], d);
-    } break;
-    case TK_DIAG1_T:
-        if (pt) {
-            const T2 d = op.m[1];
-#pragma unroll
-            for (int u = 0; u < (1 << R); u++)
-                if (active & (1u << u)) v[u] = cmul(v[u], d);
-        }
-        break;
-    case TK_DIAG_R:
-        PLB_SWITCH_P(R, (apply_diag_r<T2, R, P, false>(v, op, active, pt)));
-        break;
-    case TK_DIAG1_R:
-        PLB_SWITCH_P(R, (apply_diag_r<T2, R, P, true>(v, op, active, pt)));
-        break;
-    default: {
-        const uint32_t pb = pt ? ~op.upar : op.upar;
-        const T2 d0 = op.m[0], d1 = op.m[1];
-#pragma unroll
-        for (int u = 0; u < (1 << R); u++)
-            if (active & (1u << u)) v[u] = cmul(v[u], (pb >> u & 1) ? d1 : d0);
-    } break;
-    }
-}
-
-// Im(conj(a) b), Re(conj(a) b)
-template <typename T2> __device__ __forceinline__ double im_cb(T2 a, T2 b) {
-    return static_cast<double>(a.x) * b.y - static_cast<double>(a.y) * b.x;
-}
-template <typename T2> __device__ __forceinline__ double re_cb(T2 a, T2 b) {
-    return static_cast<double>(a.x) * b.x + static_cast<double>(a.y) * b.y;
-}
-
-template <typename T2, int R, int P, bool ISY>
-__device__ __forceinline__ double overlap_pair(const T2 (&l)[1 << R], const T2 (&h)[1 << R], uint32_t active) {
-    double s = 0;
-#pragma unroll
-    for (int q = 0; q < (1 << (R - 1)); q++) {
-        const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
-        const int u1 = u0 | (1 << P);
-        if (active & (1u << u0)) {
-            // (Y l)[u0] = -i l[u1], (Y l)[u1] = i l[u0];  (X l)[u0] = l[u1], (X l)[u1] = l[u0]
-            if constexpr (ISY) s += re_cb(h[u1], l[u0]) - re_cb(h[u0], l[u1]);
-            else s += im_cb(h[u0], l[u1]) + im_cb(h[u1], l[u0]);
-        }
-    }
-    return s;
-}
+};
 
 template <typename T2, class Cfg>
 __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
     tile_kernel(T2 *__restrict__ sv0, T2 *__restrict__ sv1, const uint64_t *__restrict__ goff_g,
                 double *__restrict__ acc_g, const __grid_constant__ PassParams<T2> pp) {
-    constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NS = Cfg::NS;
-    constexpr int NT = 1 << (M - R);
-    constexpr int NV = 1 << R;
+    using E = Exec<T2, Cfg>;
+    constexpr int M = Cfg::M, LOW = Cfg::LOW, NS = Cfg::NS, NT = E::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T2 *tile0 = reinterpret_cast<T2 *>(smem_raw);
-    T2 *tile1 = tile0 + (NS == 2 ? (1 << M) : 0);
+    unsigned char *tile0 = smem_raw;
+    unsigned char *tile1 = smem_raw + (NS == 2 ? (sizeof(T2) << M) : 0);
     uint64_t *goff = reinterpret_cast<uint64_t *>(smem_raw + NS * (sizeof(T2) << M));
     double *acc = reinterpret_cast<double *>(goff + (1 << (M - LOW)));
     static_assert(sizeof(PassParams<T2>) <= 32764, "kernel parameter space");
@@ -242,104 +64,19 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
     __syncthreads();
     const uint32_t tid = threadIdx.x;
     const int nrounds = pp.hdr.nrounds;
+    const WarpReduce red{acc};
 
     for (uint64_t t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
         const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
-        // ---- load the tile(s) (coalesced 128-byte lines)
-        {
-            T2 v[NV];
-#pragma unroll
-            for (int u = 0; u < NV; u++) {
-                const uint32_t j = tid + u * NT;
-                v[u] = sv0[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
-            }
-#pragma unroll
-            for (int u = 0; u < NV; u++) tile0[swz(tid + u * NT)] = v[u];
-            if constexpr (NS == 2) {
-#pragma unroll
-                for (int u = 0; u < NV; u++) {
-                    const uint32_t j = tid + u * NT;
-                    v[u] = sv1[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))];
-                }
-#pragma unroll
-                for (int u = 0; u < NV; u++) tile1[swz(tid + u * NT)] = v[u];
-            }
-        }
+        E::load_tile(tid, base, goff, sv0, tile0);
+        if constexpr (NS == 2) E::load_tile(tid, base, goff, sv1, tile1);
         __syncthreads();
-        // ---- rounds
         for (int r = 0; r < nrounds; r++) {
-            const RoundHdr &rh = pp.rounds[r];
-            uint32_t jbase = tid;
-#pragma unroll
-            for (int i = 0; i < R; i++) {
-                const uint32_t lm = rh.lowmask[i];
-                jbase = ((jbase & ~lm) << 1) | (jbase & lm);
-            }
-            T2 v[NV];
-            T2 h[NS == 2 ? NV : 1];
-#pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = tile0[swz(jbase | rh.roff[u])];
-            if constexpr (NS == 2) {
-#pragma unroll
-                for (int u = 0; u < NV; u++) h[u] = tile1[swz(jbase | rh.roff[u])];
-            }
-            const int k_end = rh.first_op + rh.nops;
-            for (int k = rh.first_op; k < k_end; k++) {
-                const TileOp<T2> &op = pp.ops[k];
-                if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
-                const uint32_t active = ((jbase & op.cm_thr) == op.cv_thr) ? op.umask : 0u;
-                const bool pt = ((__popc(jbase & op.pm_thr) + __popcll(base & op.pmask_o)) & 1) != 0;
-                if constexpr (NS == 2) {
-                    if (op.kind >= TK_OVL_X) {
-                        double s = 0;
-                        if (op.kind == TK_OVL_X) {
-                            PLB_SWITCH_P(R, (s = overlap_pair<T2, R, P, false>(v, h, active)));
-                        } else if (op.kind == TK_OVL_Y) {
-                            PLB_SWITCH_P(R, (s = overlap_pair<T2, R, P, true>(v, h, active)));
-                        } else {
-                            const uint32_t pb = pt ? ~op.upar : op.upar;
-                            const double g0 = op.m[0].x, g1 = op.m[0].y;
-#pragma unroll
-                            for (int u = 0; u < NV; u++)
-                                if (active & (1u << u)) s += ((pb >> u & 1) ? g1 : g0) * im_cb(h[u], v[u]);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        if ((tid & 31) == 0) atomicAdd(&acc[op.slot], s);
-                        continue;
-                    }
-                    apply_gate<T2, R>(h, op, active, pt);
-                }
-                apply_gate<T2, R>(v, op, active, pt);
-            }
-#pragma unroll
-            for (int u = 0; u < NV; u++) tile0[swz(jbase | rh.roff[u])] = v[u];
-            if constexpr (NS == 2) {
-#pragma unroll
-                for (int u = 0; u < NV; u++) tile1[swz(jbase | rh.roff[u])] = h[u];
-            }
+            E::round(pp, r, tid, base, tile0, tile1, red);
             __syncthreads();
         }
-        // ---- store the tile(s)
-        {
-            T2 v[NV];
-#pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = tile0[swz(tid + u * NT)];
-#pragma unroll
-            for (int u = 0; u < NV; u++) {
-                const uint32_t j = tid + u * NT;
-                sv0[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
-            }
-            if constexpr (NS == 2) {
-#pragma unroll
-                for (int u = 0; u < NV; u++) v[u] = tile1[swz(tid + u * NT)];
-#pragma unroll
-                for (int u = 0; u < NV; u++) {
-                    const uint32_t j = tid + u * NT;
-                    sv1[base | goff[j >> LOW] | (j & ((1u << LOW) - 1))] = v[u];
-                }
-            }
-        }
+        E::store_tile(tid, base, goff, sv0, tile0);
+        if constexpr (NS == 2) E::store_tile(tid, base, goff, sv1, tile1);
         __syncthreads();
     }
     if constexpr (NS == 2) {
@@ -347,6 +84,36 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
             if (acc[i] != 0.0) atomicAdd(&acc_g[i], acc[i]);
     }
 }
+#endif // !PLB200_HOST_EMU
+
+#if defined(PLB200_HOST_EMU)
+// Thread-by-thread execution of one pass on host memory (test-only emulation, and the reference
+// semantics of tile_kernel: threads of a round are independent, rounds are separated by barriers).
+struct HostReduce {
+    double *acc;
+    __host__ __device__ void operator()(int slot, double s) const { acc[slot] += s; }
+};
+template <typename T2, class Cfg>
+void emulate_pass(T2 *sv0, T2 *sv1, const uint64_t *goff, double *acc, const PassParams<T2> &pp) {
+    using E = Exec<T2, Cfg>;
+    std::vector<unsigned char> t0(sizeof(T2) << Cfg::M), t1(sizeof(T2) << Cfg::M);
+    const HostReduce red{acc};
+    for (uint64_t t = 0; t < pp.hdr.ntiles; t++) {
+        const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
+        for (uint32_t tid = 0; tid < static_cast<uint32_t>(E::NT); tid++) {
+            E::load_tile(tid, base, goff, sv0, t0.data());
+            if (Cfg::NS == 2) E::load_tile(tid, base, goff, sv1, t1.data());
+        }
+        for (int r = 0; r < pp.hdr.nrounds; r++)
+            for (uint32_t tid = 0; tid < static_cast<uint32_t>(E::NT); tid++)
+                E::round(pp, r, tid, base, t0.data(), t1.data(), red);
+        for (uint32_t tid = 0; tid < static_cast<uint32_t>(E::NT); tid++) {
+            E::store_tile(tid, base, goff, sv0, t0.data());
+            if (Cfg::NS == 2) E::store_tile(tid, base, goff, sv1, t1.data());
+        }
+    }
+}
+#endif // PLB200_HOST_EMU
 
 // --------------------------------------------------------------------------- host scheduler
 struct FOp {
@@ -358,6 +125,13 @@ struct FOp {
     cd d[2];
 };
 
+// the in-place LU of the tile interpreter needs an invertible block (every gate is; a user matrix or
+// a generator need not be): others run through the stand-alone kernels
+bool well_conditioned(const cd *m) {
+    const double nrm = std::norm(m[0]) + std::norm(m[1]) + std::norm(m[2]) + std::norm(m[3]);
+    return std::abs(m[0] * m[3] - m[1] * m[2]) > 1e-6 * nrm;
+}
+
 FOp classify(const COp &op) {
     FOp f;
     uint64_t t = 0;
@@ -365,7 +139,7 @@ FOp classify(const COp &op) {
     f.all = t | op.cmask | (op.parity ? op.pmask : 0);
     if (op.kind == OP_PROJECT) f.all = ~uint64_t{0};
     if (op.kind == OP_PAIRS && !op.parity && op.tbits.size() == 1 && op.blocks.size() == 1 && op.blocks[0].a == 0 &&
-        op.blocks[0].b == 1) {
+        op.blocks[0].b == 1 && well_conditioned(op.blocks[0].m)) {
         f.fusable = true;
         f.nd = t;
     } else if (op.kind == OP_DIAG) {
@@ -451,6 +225,10 @@ uint64_t grow(const std::vector<FOp> &f, const std::vector<int> &pending, uint64
     return S;
 }
 
+#if defined(PLB200_HOST_EMU)
+int64_t g_kind_hist[32] = {0}; // encoder coverage: ops emitted per kind (test-only)
+#endif
+
 struct HostPass {
     std::vector<int> tbits;               // sorted ascending, size M
     std::vector<std::vector<int>> rounds; // item indices per round
@@ -463,14 +241,76 @@ struct Step {
     size_t params = 0; // index into the params vector
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
-    std::vector<int> slots; // adjoint: global accumulator slot of each pass-local slot
+    std::vector<int> slots;          // adjoint: global accumulator slot of each pass-local slot
+    std::vector<double> slot_scale;  // ... and the |pending scalar|^2 its overlap was taken under
 };
 
+// In-place form of a 2x2 block (tile_exec.cuh): kind, packed parameters, the scalar s that is left
+// for the host to carry (only when fold is allowed, else 1) and whether an X must precede it (pivot).
+struct PairForm {
+    int kind = K_LU_C;
+    bool pre_swap = false;
+    cd s{1.0, 0.0};
+    cd m[4];
+};
+inline bool is_real(cd z) { return z.imag() == 0.0; }
+inline bool is_imag(cd z) { return z.real() == 0.0; }
+
+PairForm pair_form(const cd *min, bool fold) {
+    PairForm f;
+    cd m[4] = {min[0], min[1], min[2], min[3]};
+    if (m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0)) {
+        f.kind = K_SWAP;
+        return f;
+    }
+    const bool all_real = is_real(m[0]) && is_real(m[1]) && is_real(m[2]) && is_real(m[3]);
+    const bool rx_like = is_real(m[0]) && is_real(m[3]) && is_imag(m[1]) && is_imag(m[2]);
+    // rotations [[c, -s], [s, c]] / [[c, -is], [-is, c]] with c^2 + s^2 = 1: three shears
+    //   [[1, u], [0, 1]] [[1, 0], [l, 1]] [[1, u], [0, 1]],  l = s, u = -s / (1 + c)   (c >= 0)
+    // (c < 0: rotate by the angle - pi instead and carry the sign, if a global scalar may be carried)
+    if (all_real && m[0] == m[3] && m[1] == -m[2]) {
+        double c = m[0].real(), sn = m[2].real();
+        if (std::abs(c * c + sn * sn - 1.0) <= 8e-16 && (c >= 0.0 || fold)) {
+            if (c < 0.0) c = -c, sn = -sn, f.s = -1.0;
+            f.kind = K_LIFT_R, f.m[0] = cd(-sn / (1.0 + c), sn);
+            return f;
+        }
+    }
+    if (rx_like && m[0] == m[3] && m[1] == m[2]) {
+        double c = m[0].real(), sn = -m[2].imag();
+        if (std::abs(c * c + sn * sn - 1.0) <= 8e-16 && (c >= 0.0 || fold)) {
+            if (c < 0.0) c = -c, sn = -sn, f.s = -1.0;
+            f.kind = K_LIFT_I, f.m[0] = cd(-sn / (1.0 + c), -sn);
+            return f;
+        }
+    }
+    if (fold && all_real && m[0] == m[1] && m[0] == m[2] && m[0] == -m[3] && m[0] != cd(0.0)) {
+        f.kind = K_HAD, f.s = m[0];
+        return f;
+    }
+    // LU with column pivoting: M = diag(al, be) [[1, 0], [t2, 1]] [[1, t1], [0, 1]] (after an X if |m01| > |m00|)
+    if (std::abs(m[1]) > std::abs(m[0])) {
+        f.pre_swap = true;
+        std::swap(m[0], m[1]);
+        std::swap(m[2], m[3]);
+    }
+    const cd al = m[0], t1 = m[1] / m[0], be = (m[0] * m[3] - m[1] * m[2]) / m[0], t2 = m[2] / be;
+    if (all_real) f.kind = K_LU_R, f.m[0] = cd(t1.real(), t2.real()), f.m[1] = cd(al.real(), be.real());
+    else f.kind = K_LU_C, f.m[0] = t1, f.m[1] = t2, f.m[2] = al, f.m[3] = be;
+    return f;
+}
+
 // Pure host: schedule `items` on an n-qubit state into tile passes / stand-alone items.
+// allow_scaled: uncontrolled rotations / diagonals may leave a scalar factor with the host (sigma),
+// which is multiplied back into the state by a K_DIAG_T op before it can over/underflow, at the end
+// of every adjoint pass, and at the end of the tape.
 template <typename T2, class Cfg>
-void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std::vector<Step> &steps,
-                    std::vector<unsigned char> &arena, std::vector<PassParams<T2>> &params) {
-    constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R;
+void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled,
+                    std::vector<Step> &steps, std::vector<unsigned char> &arena,
+                    std::vector<PassParams<T2>> &params) {
+    constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NTB = M - R, SB = Swz<T2>::B;
+    constexpr bool is_double = sizeof(T2) == 16;
+    const double sig_lo = is_double ? 0x1p-200 : 0x1p-20, sig_hi = is_double ? 0x1p200 : 0x1p20;
     steps.clear();
     arena.clear();
     params.clear();
@@ -492,7 +332,18 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std:
     size_t first = 0;
     const size_t window = 512;
     const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
+    const size_t max_pass_ops = kMaxPassOps - kMaxPassRounds - 2; // emitted ops; room for the scalar ops
     std::vector<int> pending, exec;
+    cd sigma{1.0, 0.0};
+    int last_pass_step = -1;
+
+    auto scale_op = [](cd s) {
+        TileOp<T2> t;
+        std::memset(&t, 0, sizeof(t));
+        t.code = make_code(K_DIAG_T, 0, 0);
+        t.m[0] = t.m[1] = mk<T2>(s.real(), s.imag());
+        return t;
+    };
 
     while (true) {
         while (first < items.size() && done[first]) first++;
@@ -513,7 +364,17 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std:
         // pad T to exactly M bits with the lowest free bits
         for (int b = 0; b < n && __builtin_popcountll(T) < M; b++) T |= uint64_t{1} << b;
         simulate(f, pending, T, full, exec);
-        if (exec.size() > static_cast<size_t>(kMaxPassOps)) exec.resize(kMaxPassOps); // a prefix stays valid
+        {
+            // cap the EMITTED ops (a pivoted 2x2 block emits two); a prefix stays valid
+            size_t emitted = 0, keep = 0;
+            for (int i : exec) {
+                const AdjItem &it = items[i];
+                emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
+                if (emitted > max_pass_ops) break;
+                keep++;
+            }
+            exec.resize(keep);
+        }
         std::vector<int> pass_ops = exec;
 
         // ---- rounds
@@ -524,7 +385,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std:
         while (!rem.empty()) {
             uint64_t seed = f[rem[0]].nd; // guarantees progress
             uint64_t Rb = grow(f, rem, seed, R, T, full, rexec);
-            // pad to R bits with tile bits (prefer high local bits: conflict-free shared accesses)
+            // pad to R bits with tile bits (prefer high local bits)
             for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < R; i--) Rb |= uint64_t{1} << hp.tbits[i];
             simulate(f, rem, Rb, full, rexec);
             if (rexec.empty()) fail("fusion scheduler made no progress");
@@ -555,7 +416,6 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std:
         RoundHdr *rh = params.back().rounds;
         TileOp<T2> *top = params.back().ops;
         hdr->nrounds = static_cast<int>(hp.rounds.size());
-        hdr->nops_total = static_cast<int>(pass_ops.size());
         hdr->ntiles = uint64_t{1} << (n - M);
         hdr->tile_ins.n = 0;
         for (int b : hp.tbits) hdr->tile_ins.lowmask[hdr->tile_ins.n++] = (uint64_t{1} << b) - 1;
@@ -580,86 +440,204 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, std:
             std::vector<int> rl; // local positions of the register bits, ascending
             for (int i = 0; i < M; i++)
                 if (hp.round_bits[r] >> hp.tbits[i] & 1) rl.push_back(i);
+            uint32_t rmask_l = 0;
+            for (int i = 0; i < R; i++) rmask_l |= 1u << rl[i];
+            // ---- thread-bit assignment.  Low SB lane bits: tile bits with independent swizzle
+            // columns (conflict-free shared accesses), taken first from the bits no op of this round
+            // uses as a control / parity bit; the most used ones end up in the warp-index bits, so
+            // conditional ops diverge as little as possible.
+            int use[32] = {0};
+            for (int idx : hp.rounds[r]) {
+                const AdjItem &it = items[idx];
+                const uint64_t cm = it.overlap ? it.pw.cmask : it.op.cmask;
+                const uint64_t pm = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : f[idx].pmask);
+                const uint32_t l = to_local((cm | pm) & T) & ~rmask_l;
+                for (int i = 0; i < M; i++)
+                    if (l >> i & 1) use[i]++;
+            }
+            std::vector<int> nr;
+            for (int i = 0; i < M; i++)
+                if (!(rmask_l >> i & 1)) nr.push_back(i);
+            std::stable_sort(nr.begin(), nr.end(), [&](int a, int b) { return use[a] < use[b]; });
+            auto col_of = [&](int bit) { return bit < SB ? (1u << bit) : swz_col<T2>(bit); };
+            std::vector<int> tpos;
+            {
+                uint32_t basis[4] = {0, 0, 0, 0}; // reduced basis by leading bit
+                std::vector<char> taken(M, 0);
+                for (int cand : nr) {
+                    if (static_cast<int>(tpos.size()) == SB) break;
+                    uint32_t c = col_of(cand);
+                    for (int b = SB - 1; b >= 0 && c; b--)
+                        if ((c >> b & 1) && basis[b]) c ^= basis[b];
+                    if (!c) continue;
+                    basis[31 - __builtin_clz(c)] = c;
+                    tpos.push_back(cand), taken[cand] = 1;
+                }
+                for (int cand : nr)
+                    if (!taken[cand]) tpos.push_back(cand);
+            }
             rh[r].first_op = op_cursor;
-            rh[r].nops = static_cast<int>(hp.rounds[r].size());
-            for (int i = 0; i < R; i++) rh[r].lowmask[i] = (1u << rl[i]) - 1;
+            for (int i = 0; i < NTB; i++) rh[r].w[i] = swz<T2>(1u << tpos[i]) * static_cast<uint32_t>(sizeof(T2));
             for (int u = 0; u < (1 << R); u++) {
                 uint32_t o = 0;
                 for (int i = 0; i < R; i++)
                     if (u >> i & 1) o |= 1u << rl[i];
-                rh[r].roff[u] = o;
+                rh[r].sroff[u] = swz<T2>(o) * static_cast<uint32_t>(sizeof(T2));
             }
-            uint32_t rmask_l = 0;
-            for (int i = 0; i < R; i++) rmask_l |= 1u << rl[i];
+            auto to_tid = [&](uint32_t local_mask) {
+                uint32_t m = 0;
+                for (int i = 0; i < NTB; i++)
+                    if (local_mask >> tpos[i] & 1) m |= 1u << i;
+                return m;
+            };
+            auto reg_of_local = [&](int lp) { return static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin()); };
+            auto reg_pos = [&](int global_bit) { return reg_of_local(local_of[global_bit]); };
+            auto roff_of = [&](int u) {
+                uint32_t o = 0;
+                for (int i = 0; i < R; i++)
+                    if (u >> i & 1) o |= 1u << rl[i];
+                return o;
+            };
+
             for (int idx : hp.rounds[r]) {
                 const AdjItem &it = items[idx];
                 const FOp &fo = f[idx];
-                TileOp<T2> &t = top[op_cursor++];
-                const uint64_t cmask = it.overlap ? it.pw.cmask : it.op.cmask;
-                const uint64_t cval = it.overlap ? it.pw.cval : it.op.cval;
-                const uint64_t pmask = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : fo.pmask);
-                const uint32_t cm_l = to_local(cmask & T), cv_l = to_local(cval & T), pm_l = to_local(pmask & T);
-                t.cm_thr = cm_l & ~rmask_l, t.cv_thr = cv_l & ~rmask_l;
-                t.cmask_o = cmask & ~T, t.cval_o = cval & ~T;
-                t.pm_thr = pm_l & ~rmask_l;
-                t.pmask_o = pmask & ~T;
-                t.umask = 0, t.upar = 0;
-                for (int u = 0; u < (1 << R); u++) {
-                    const uint32_t ro = rh[r].roff[u];
-                    if ((ro & cm_l) == (cv_l & rmask_l)) t.umask |= 1u << u;
-                    if (__builtin_popcount(ro & pm_l) & 1) t.upar |= 1u << u;
+                TileOp<T2> t;
+                std::memset(&t, 0, sizeof(t));
+                uint64_t cmask = it.overlap ? it.pw.cmask : it.op.cmask;
+                uint64_t cval = it.overlap ? it.pw.cval : it.op.cval;
+                uint64_t pmask = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : fo.pmask);
+                cd d0 = fo.d[0], d1 = fo.d[1];
+                const bool is_diag = !it.overlap && it.op.kind != OP_PAIRS;
+                if (is_diag) {
+                    if (pmask == 0) { // one scalar d0 == d1 on the control subspace
+                        if (cmask == 0 && allow_scaled) {
+                            sigma *= d0; // global phase: nothing to do on the device
+                            continue;
+                        }
+                        // turn one value-1 control into the parity bit: diag(1, d) on it
+                        const uint64_t ones = cmask & cval;
+                        if (ones) {
+                            uint64_t pick = 0;
+                            for (int i = 0; i < R && !pick; i++)
+                                if (ones >> hp.tbits[rl[i]] & 1) pick = uint64_t{1} << hp.tbits[rl[i]];
+                            if (!pick && (ones & T)) pick = uint64_t{1} << __builtin_ctzll(ones & T);
+                            if (!pick) pick = uint64_t{1} << __builtin_ctzll(ones);
+                            pmask = pick, cmask &= ~pick, cval &= ~pick;
+                            d1 = d0, d0 = cd(1.0);
+                        }
+                    }
+                    if (d0 != cd(1.0) && cmask == 0 && allow_scaled && pmask != 0) {
+                        sigma *= d0;
+                        d1 /= d0, d0 = cd(1.0);
+                    }
                 }
-                auto reg_pos = [&](int global_bit) {
-                    const int lp = local_of[global_bit];
-                    return static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
-                };
+                const uint32_t cm_l = to_local(cmask & T), cv_l = to_local(cval & T), pm_l = to_local(pmask & T);
+                const uint32_t cm_reg = cm_l & rmask_l, pm_reg = pm_l & rmask_l;
+                t.cm_tid = to_tid(cm_l & ~rmask_l), t.cv_tid = to_tid(cv_l & ~rmask_l);
+                t.pm_tid = to_tid(pm_l & ~rmask_l);
+                t.cmask_o = cmask & ~T, t.cval_o = cval & ~T, t.pmask_o = pmask & ~T;
+                uint32_t umask = 0, upar = 0;
+                for (int u = 0; u < (1 << R); u++) {
+                    const uint32_t ro = roff_of(u);
+                    if ((ro & cm_l) == (cv_l & rmask_l)) umask |= 1u << u;
+                    if (__builtin_popcount(ro & pm_l) & 1) upar |= 1u << u;
+                }
+                t.umask = static_cast<uint16_t>(umask), t.upar = static_cast<uint16_t>(upar);
+                const bool one_ctrl_reg = __builtin_popcount(cm_reg) == 1 && (cv_l & cm_reg) == cm_reg;
+                const int creg = cm_reg ? reg_of_local(__builtin_ctz(cm_reg)) : 0;
                 if (it.overlap) {
-                    t.slot = static_cast<uint32_t>(st.slots.size());
+                    t.slot = static_cast<uint16_t>(st.slots.size());
                     st.slots.push_back(it.slot);
+                    st.slot_scale.push_back(std::norm(sigma));
                     if (it.pw.x) {
-                        t.kind = (it.pw.z == it.pw.x) ? TK_OVL_Y : TK_OVL_X;
-                        t.p = reg_pos(__builtin_ctzll(it.pw.x));
+                        t.code = make_code((it.pw.z == it.pw.x) ? K_OVL_Y : K_OVL_X, reg_pos(__builtin_ctzll(it.pw.x)), 0);
                     } else {
-                        t.kind = TK_OVL_D;
+                        t.code = make_code(K_OVL_D, 0, 0);
                         t.m[0] = mk<T2>(1.0, it.pw.z ? -1.0 : 1.0);
                     }
                 } else if (it.op.kind == OP_PAIRS) {
-                    const cd *m = it.op.blocks[0].m;
-                    t.kind = TK_GENERAL;
-                    if (m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0)) t.kind = TK_SWAP;
-                    else if (m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0)
-                        t.kind = TK_REAL;
-                    else if (m[0].imag() == 0 && m[3].imag() == 0 && m[1].real() == 0 && m[2].real() == 0)
-                        t.kind = TK_RXLIKE;
-                    t.p = reg_pos(it.op.tbits[0]);
-                    for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(m[q].real(), m[q].imag());
+                    const int p = reg_pos(it.op.tbits[0]);
+                    const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0);
+                    const bool masked = cm_reg != 0;
+                    auto masked_kind = [](int k) {
+                        return k == K_LIFT_R ? K_LIFT_R_M : k == K_LIFT_I ? K_LIFT_I_M : k == K_LU_R ? K_LU_R_M
+                               : k == K_LU_C ? K_LU_C_M : K_SWAP_M;
+                    };
+                    const int swap_kind = !masked ? K_SWAP : one_ctrl_reg ? K_SWAP_CR : K_SWAP_M;
+                    if (pf.pre_swap) { // pivot: X first, same controls
+                        TileOp<T2> x = t;
+                        x.code = make_code(swap_kind, p, swap_kind == K_SWAP_CR ? creg : 0);
+                        top[op_cursor++] = x;
+                    }
+                    int kind = pf.kind, c = 0;
+                    if (kind == K_SWAP) kind = swap_kind, c = (swap_kind == K_SWAP_CR ? creg : 0);
+                    else if (masked) kind = masked_kind(kind);
+                    sigma *= pf.s;
+                    t.code = make_code(kind, p, c);
+                    for (int q = 0; q < 4; q++) t.m[q] = mk<T2>(pf.m[q].real(), pf.m[q].imag());
                 } else {
-                    const bool one = (fo.d[0] == cd(1.0));
-                    const uint32_t pr = pm_l & rmask_l;
-                    if (pr == 0) t.kind = one ? TK_DIAG1_T : TK_DIAG_T;
-                    else if (__builtin_popcount(pr) == 1) {
-                        t.kind = one ? TK_DIAG1_R : TK_DIAG_R;
-                        const int lp = __builtin_ctz(pr);
-                        t.p = static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin());
-                    } else
-                        t.kind = TK_DIAG_G;
-                    t.m[0] = mk<T2>(fo.d[0].real(), fo.d[0].imag());
-                    t.m[1] = mk<T2>(fo.d[1].real(), fo.d[1].imag());
+                    const bool one = (d0 == cd(1.0));
+                    const int npr = __builtin_popcount(pm_reg);
+                    const int p0 = npr >= 1 ? reg_of_local(__builtin_ctz(pm_reg)) : 0;
+                    const int p1 = npr >= 2 ? reg_of_local(31 - __builtin_clz(pm_reg)) : 0;
+                    if (cm_reg == 0 && npr == 0) t.code = make_code(one ? K_DIAG1_T : K_DIAG_T, 0, 0);
+                    else if (cm_reg == 0 && npr == 1)
+                        t.code = make_code((one && t.pm_tid == 0 && t.pmask_o == 0) ? K_DIAG1_R : K_DIAG_R, p0, 0);
+                    else if (cm_reg == 0 && npr == 2) t.code = make_code(K_DIAG_PP, p0, p1);
+                    else if (one_ctrl_reg && npr == 0) t.code = make_code(K_DIAG_CT, creg, 0);
+                    else if (one_ctrl_reg && npr == 1) t.code = make_code(K_DIAG_CR, p0, creg);
+                    else t.code = make_code(K_DIAG_G, 0, 0);
+                    t.m[0] = mk<T2>(d0.real(), d0.imag());
+                    t.m[1] = mk<T2>(d1.real(), d1.imag());
                 }
+#if defined(PLB200_HOST_EMU)
+                g_kind_hist[(t.code >> 4) & 31]++;
+#endif
+                top[op_cursor++] = t;
             }
+            const bool last_round = r + 1 == hp.rounds.size();
+            const double mag = std::abs(sigma);
+            if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && Cfg::NS == 2))) {
+                top[op_cursor++] = scale_op(sigma);
+                sigma = cd(1.0);
+            }
+            rh[r].nops = op_cursor - rh[r].first_op;
         }
+        hdr->nops_total = op_cursor;
         hdr->nslots = static_cast<int>(st.slots.size());
         st.off = off;
         st.params = params.size() - 1;
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
-        st.nrounds = hdr->nrounds, st.nops = hdr->nops_total;
+        st.nrounds = hdr->nrounds, st.nops = static_cast<int>(pass_ops.size());
+        last_pass_step = static_cast<int>(steps.size());
         steps.push_back(std::move(st));
+    }
+    if (sigma != cd(1.0)) {
+        // a scalar commutes with everything that follows: multiply it back in the last pass
+        if (last_pass_step < 0) fail("fusion: pending scalar without a tile pass");
+        PassParams<T2> &pp = params[steps[last_pass_step].params];
+        RoundHdr &rr = pp.rounds[pp.hdr.nrounds - 1];
+        pp.ops[pp.hdr.nops_total++] = scale_op(sigma);
+        rr.nops++;
     }
 }
 
 template <class Cfg, typename T2> size_t smem_bytes_for() {
     return Cfg::NS * (sizeof(T2) << Cfg::M) + (sizeof(uint64_t) << (Cfg::M - Cfg::LOW)) +
            (Cfg::NS == 2 ? sizeof(double) * kMaxPassOps : 0);
+}
+
+std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
+    std::vector<AdjItem> items(ops.size());
+    for (size_t i = 0; i < ops.size(); i++) items[i].op = ops[i];
+    return items;
+}
+
+#if !defined(PLB200_HOST_EMU)
+bool scaled_forms_enabled() {
+    const char *e = std::getenv("PLB200_FUSE_SCALED");
+    return !(e && e[0] == '0');
 }
 
 template <typename T2, class Cfg> void prepare_kernel() {
@@ -671,19 +649,13 @@ template <typename T2, class Cfg> void prepare_kernel() {
     done = true;
 }
 
-std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
-    std::vector<AdjItem> items(ops.size());
-    for (size_t i = 0; i < ops.size(); i++) items[i].op = ops[i];
-    return items;
-}
-
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
     using Cfg = FwdCfg<T2>;
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
     std::vector<PassParams<T2>> params;
     const auto items = as_items(ops);
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, steps, arena, params);
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), steps, arena, params);
     // ---- upload every pass's offset table once, then launch the whole schedule back to back
     unsigned char *dplan = nullptr;
     if (!arena.empty()) {
@@ -712,7 +684,8 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
     std::vector<Step> steps;
     std::vector<unsigned char> arena;
     std::vector<PassParams<T2>> params;
-    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, steps, arena, params);
+    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), steps, arena,
+                            params);
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
     // device accumulators: one slab of kMaxPassOps doubles per tile pass
     size_t n_pass = 0;
@@ -761,12 +734,14 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         pass_idx = 0;
         for (const Step &st : steps) {
             if (st.op >= 0) continue;
-            for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += h[pass_idx * kMaxPassOps + s];
+            for (size_t s = 0; s < st.slots.size(); s++)
+                acc_host[st.slots[s]] += st.slot_scale[s] * h[pass_idx * kMaxPassOps + s];
             pass_idx++;
         }
     } else
         lambda.sync();
 }
+#endif // !PLB200_HOST_EMU
 
 } // namespace
 
@@ -776,10 +751,10 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
     const auto items = as_items(ops);
     if (precision == 64) {
         std::vector<PassParams<double2>> params;
-        build_schedule<double2, FwdCfg<double2>>(n, 148, items, steps, arena, params);
+        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, steps, arena, params);
     } else {
         std::vector<PassParams<float2>> params;
-        build_schedule<float2, FwdCfg<float2>>(n, 148, items, steps, arena, params);
+        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, steps, arena, params);
     }
     out[0] = out[1] = out[2] = out[3] = 0;
     for (const auto &s : steps) {
@@ -788,6 +763,43 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
     }
 }
 
+bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const std::vector<int64_t> &tp,
+                         int64_t num_param_ops, std::vector<AdjItem> &items, std::vector<double> &sfs) {
+    const int64_t n_tp = static_cast<int64_t>(tp.size());
+    items.clear();
+    sfs.assign(n_tp, 0.0);
+    int64_t tpi = n_tp - 1, cur = num_param_ops - 1;
+    for (int64_t op_idx = static_cast<int64_t>(calls.size()) - 1; op_idx >= 0; op_idx--) {
+        const GateCall &c = calls[op_idx];
+        PLB_CHECK(c.params.size() <= 1, "The operation is not supported using the adjoint differentiation method");
+        if (c.name == "StatePrep" || c.name == "BasisState") continue;
+        if (tpi < 0) break;
+        if (!c.params.empty()) {
+            if (cur == tp[tpi]) {
+                AdjItem it;
+                it.overlap = true;
+                double gscale = 0;
+                if (!generator_as_pauli(n, c, &it.pw, &gscale)) return false;
+                it.slot = static_cast<int>(tpi);
+                sfs[tpi] = gscale * (c.inverse ? -1.0 : 1.0);
+                items.push_back(std::move(it));
+                tpi--;
+            }
+            cur--;
+        }
+        if (tpi < 0) break;
+        GateCall inv = c;
+        inv.inverse = !c.inverse;
+        for (auto &lo : lower_gate(n, inv)) {
+            AdjItem it;
+            it.op = std::move(lo);
+            items.push_back(std::move(it));
+        }
+    }
+    return true;
+}
+
+#if !defined(PLB200_HOST_EMU)
 void run_fused(StateVec &sv, const std::vector<COp> &ops) {
     sv.set_device();
     if (sv.precision == 64) run_fused_typed<double2>(sv, ops);
@@ -801,5 +813,58 @@ void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
     if (lambda.precision == 64) run_adjoint_typed<double2>(lambda, hl, items, n_slots, acc_host, stats);
     else run_adjoint_typed<float2>(lambda, hl, items, n_slots, acc_host, stats);
 }
+#else
+// ------------------------------------------------------------------------------------------
+// Test-only host emulation (libplb200_emu.so): the same schedule + encoder + per-thread code,
+// executed on host memory.  Stand-alone steps are reported back to the caller (the Python test
+// applies them with the numpy oracle), tile passes run through emulate_pass().
+template <typename T2, class Cfg>
+int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0, T2 *sv1, double *acc_host,
+                  int n_slots, int (*standalone)(void *, int), void *ctx, int64_t stats[4]) {
+    std::vector<Step> steps;
+    std::vector<unsigned char> arena;
+    std::vector<PassParams<T2>> params;
+    build_schedule<T2, Cfg>(n, 148, items, scaled, steps, arena, params);
+    for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (const Step &st : steps) {
+        if (st.op >= 0) {
+            stats[1]++;
+            if (standalone(ctx, st.op) != 0) return 1;
+            continue;
+        }
+        std::vector<double> acc(kMaxPassOps, 0.0);
+        emulate_pass<T2, Cfg>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off), acc.data(),
+                              params[st.params]);
+        for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
+        stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
+    }
+    return 0;
+}
+void emu_kind_hist(int64_t out[32], bool reset) {
+    for (int i = 0; i < 32; i++) {
+        out[i] = g_kind_hist[i];
+        if (reset) g_kind_hist[i] = 0;
+    }
+}
+int emulate_fused(int n, int precision, const std::vector<AdjItem> &items, bool adjoint, bool scaled, void *sv0,
+                  void *sv1, double *acc_host, int n_slots, int (*standalone)(void *, int), void *ctx,
+                  int64_t stats[4]) {
+    if (precision == 64) {
+        if (adjoint)
+            return emulate_typed<double2, AdjCfg<double2>>(n, items, scaled, static_cast<double2 *>(sv0),
+                                                           static_cast<double2 *>(sv1), acc_host, n_slots, standalone,
+                                                           ctx, stats);
+        return emulate_typed<double2, FwdCfg<double2>>(n, items, scaled, static_cast<double2 *>(sv0), nullptr,
+                                                       acc_host, n_slots, standalone, ctx, stats);
+    }
+    if (adjoint)
+        return emulate_typed<float2, AdjCfg<float2>>(n, items, scaled, static_cast<float2 *>(sv0),
+                                                     static_cast<float2 *>(sv1), acc_host, n_slots, standalone, ctx,
+                                                     stats);
+    return emulate_typed<float2, FwdCfg<float2>>(n, items, scaled, static_cast<float2 *>(sv0), nullptr, acc_host,
+                                                 n_slots, standalone, ctx, stats);
+}
+#endif
 
 } // namespace plb200

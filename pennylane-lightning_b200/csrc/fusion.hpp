@@ -19,6 +19,12 @@ struct AdjItem {
     PauliWordMask pw;
     int slot = -1;
 };
+// Backward-sweep item list of the adjoint method (AdjointJacobianLQubit.hpp:269-314): for every op,
+// last to first, [overlap with its generator if it is the next trainable one] then [its inverse].
+// sfs[p] = generator scale factor x (-1 for inverse ops).  Returns false when a trainable generator is
+// not a (controlled) Pauli word (the caller then uses the copy + generator + dot route).
+bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const std::vector<int64_t> &tp,
+                         int64_t num_param_ops, std::vector<AdjItem> &items, std::vector<double> &sfs);
 // Runs the items in order on the pair (lambda, H lambda) with tile passes over both states;
 // acc_host[slot] receives Im<H lambda|P|lambda>.  stats = {tile passes, stand-alone items, fused items}.
 void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,

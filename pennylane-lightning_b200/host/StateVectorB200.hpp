@@ -7,6 +7,7 @@
 #include <complex>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -86,7 +87,7 @@ template <class Precision = double> class StateVectorB200 {
         CopyHostDataToGpu(host_data, length, false);
     }
     StateVectorB200(const StateVectorB200 &other) : StateVectorB200(other.num_qubits_, other.dev_tag_) {
-        PLB200_ABI(plb200_sv_d2d(h_, other.h_));
+        PLB200_ABI(plb200_sv_d2d(h_, other.handle()));
     }
     StateVectorB200 &operator=(const StateVectorB200 &) = delete;
     StateVectorB200(StateVectorB200 &&o) noexcept : h_{o.h_}, num_qubits_{o.num_qubits_}, dev_tag_{o.dev_tag_} {
@@ -100,15 +101,46 @@ template <class Precision = double> class StateVectorB200 {
     [[nodiscard]] auto getNumQubits() const -> std::size_t { return num_qubits_; }
     [[nodiscard]] auto getTotalNumQubits() const -> std::size_t { return num_qubits_; }
     [[nodiscard]] auto getLength() const -> std::size_t { return std::size_t{1} << num_qubits_; }
-    [[nodiscard]] auto getData() -> CFP_t * { return static_cast<CFP_t *>(plb200_sv_device_ptr(h_)); }
-    [[nodiscard]] auto getData() const -> const CFP_t * { return static_cast<const CFP_t *>(plb200_sv_device_ptr(h_)); }
+    [[nodiscard]] auto getData() -> CFP_t * {
+        flush();
+        return static_cast<CFP_t *>(plb200_sv_device_ptr(h_));
+    }
+    [[nodiscard]] auto getData() const -> const CFP_t * {
+        flush();
+        return static_cast<const CFP_t *>(plb200_sv_device_ptr(h_));
+    }
     [[nodiscard]] auto getDevTag() const -> const DevTag<int> & { return dev_tag_; }
-    [[nodiscard]] plb200_sv *handle() const { return h_; }
+    // Every consumer of the device state (measurements, observables, adjoint, copies) goes through
+    // handle(): pending gates are flushed first.
+    [[nodiscard]] plb200_sv *handle() const {
+        flush();
+        return h_;
+    }
+    // Lazy gate queue: the per-gate API (one Python->C++ call per gate, Bindings.hpp:223-276) only
+    // validates and records the gate; the queue is applied as ONE fused tape on the first read.
+    // PLB200_LAZY=0 restores one kernel launch per call.
+    void flush() const {
+        if (queue_.names.empty()) return;
+        auto v = queue_.view();
+        detail::OpsBlob done;
+        std::swap(done, queue_); // queue_ is empty again even if the call throws
+        v = done.view();
+        PLB200_ABI(plb200_sv_apply_ops(h_, &v, 1));
+    }
+    [[nodiscard]] std::size_t pendingOps() const { return queue_.names.size(); }
 
     void applyOperation(const std::string &opName, const std::vector<std::size_t> &wires, bool inverse = false,
                         const std::vector<PrecisionT> &params = {}) {
         const auto w = detail::to_i64(wires);
         const auto p = detail::to_f64(params);
+        if (lazy_) {
+            PLB200_ABI(plb200_validate_op(static_cast<int64_t>(num_qubits_), opName.c_str(), nullptr, nullptr, 0,
+                                          w.data(), static_cast<int64_t>(w.size()), inverse, p.data(),
+                                          static_cast<int64_t>(p.size())));
+            queue_.template add<PrecisionT>(opName, wires, inverse, params);
+            if (queue_.names.size() >= kMaxQueue) flush();
+            return;
+        }
         PLB200_ABI(plb200_sv_apply(h_, opName.c_str(), nullptr, nullptr, 0, w.data(), static_cast<int64_t>(w.size()),
                                    inverse, p.data(), static_cast<int64_t>(p.size())));
     }
@@ -120,6 +152,14 @@ template <class Precision = double> class StateVectorB200 {
         const auto w = detail::to_i64(wires), cw = detail::to_i64(controlled_wires);
         const auto cv = detail::to_u8(controlled_values);
         const auto p = detail::to_f64(params);
+        if (lazy_) {
+            PLB200_ABI(plb200_validate_op(static_cast<int64_t>(num_qubits_), opName.c_str(), cw.data(), cv.data(),
+                                          static_cast<int64_t>(cw.size()), w.data(), static_cast<int64_t>(w.size()),
+                                          inverse, p.data(), static_cast<int64_t>(p.size())));
+            queue_.template add<PrecisionT>(opName, wires, inverse, params, controlled_wires, controlled_values);
+            if (queue_.names.size() >= kMaxQueue) flush();
+            return;
+        }
         PLB200_ABI(plb200_sv_apply(h_, opName.c_str(), cw.data(), cv.data(), static_cast<int64_t>(cw.size()), w.data(),
                                    static_cast<int64_t>(w.size()), inverse, p.data(),
                                    static_cast<int64_t>(p.size())));
@@ -154,6 +194,7 @@ template <class Precision = double> class StateVectorB200 {
                                                  "parameters must all be equal");
         PLB200_ABORT_IF(n != ops_params.size(), "Invalid arguments: number of operations, wires, inverses, and "
                                                 "parameters must all be equal");
+        flush();
         detail::OpsBlob blob;
         for (std::size_t i = 0; i < n; i++) blob.add<PrecisionT>(ops[i], ops_wires[i], ops_adjoint[i], ops_params[i]);
         const auto v = blob.view();
@@ -164,11 +205,13 @@ template <class Precision = double> class StateVectorB200 {
         applyOperations(ops, ops_wires, ops_adjoint, std::vector<std::vector<PrecisionT>>(ops.size()));
     }
     void applyOperations(detail::OpsBlob &blob, bool fuse = true) {
+        flush();
         const auto v = blob.view();
         PLB200_ABI(plb200_sv_apply_ops(h_, &v, fuse ? 1 : 0));
     }
 
     void applyMatrix(const ComplexT *matrix, const std::vector<std::size_t> &wires, bool inverse = false) {
+        flush();
         PLB200_ABORT_IF(wires.empty(), "Number of wires must be larger than 0");
         const auto w = detail::to_i64(wires);
         const auto m = detail::to_c128(matrix, std::size_t{1} << (2 * wires.size()));
@@ -183,6 +226,7 @@ template <class Precision = double> class StateVectorB200 {
     void applyControlledMatrix(const ComplexT *matrix, const std::vector<std::size_t> &controlled_wires,
                                const std::vector<bool> &controlled_values, const std::vector<std::size_t> &wires,
                                bool inverse = false) {
+        flush();
         PLB200_ABORT_IF(wires.empty(), "Number of wires must be larger than 0");
         PLB200_ABORT_IF_NOT(controlled_wires.size() == controlled_values.size(),
                             "`controlled_wires` must have the same size as `controlled_values`.");
@@ -194,6 +238,7 @@ template <class Precision = double> class StateVectorB200 {
     }
     void applyPauliRot(const std::vector<std::size_t> &wires, bool inverse, const std::vector<PrecisionT> &params,
                        const std::string &word) {
+        flush();
         PLB200_ABORT_IF_NOT(wires.size() == word.size(), "wires and word have incompatible dimensions.");
         PLB200_ABORT_IF(params.empty(), "PauliRot needs one parameter");
         const auto w = detail::to_i64(wires);
@@ -202,6 +247,7 @@ template <class Precision = double> class StateVectorB200 {
     }
     [[nodiscard]] auto applyGenerator(const std::string &opName, const std::vector<std::size_t> &wires,
                                       bool adj = false) -> PrecisionT {
+        flush();
         const auto w = detail::to_i64(wires);
         double scale = 0;
         PLB200_ABI(plb200_sv_apply_generator(h_, opName.c_str(), nullptr, nullptr, 0, w.data(),
@@ -211,6 +257,7 @@ template <class Precision = double> class StateVectorB200 {
     [[nodiscard]] auto applyGenerator(const std::string &opName, const std::vector<std::size_t> &controlled_wires,
                                       const std::vector<bool> &controlled_values,
                                       const std::vector<std::size_t> &wires, bool adj = false) -> PrecisionT {
+        flush();
         const auto w = detail::to_i64(wires), cw = detail::to_i64(controlled_wires);
         const auto cv = detail::to_u8(controlled_values);
         double scale = 0;
@@ -220,16 +267,24 @@ template <class Precision = double> class StateVectorB200 {
     }
 
     // ---- state preparation (Bindings.hpp:883-921) -----------------------------------------
-    void resetStateVector(bool = false) { PLB200_ABI(plb200_sv_reset(h_)); }
+    void resetStateVector(bool = false) {
+        queue_ = detail::OpsBlob{}; // pending gates are overwritten anyway
+        PLB200_ABI(plb200_sv_reset(h_));
+    }
     void setBasisState(const std::vector<std::size_t> &state, const std::vector<std::size_t> &wires, bool = false) {
         PLB200_ABORT_IF(state.size() != wires.size(), "state and wires must have equal dimensions.");
+        queue_ = detail::OpsBlob{};
         const auto s = detail::to_i64(state), w = detail::to_i64(wires);
         PLB200_ABI(plb200_sv_set_basis_state(h_, s.data(), w.data(), static_cast<int64_t>(w.size())));
     }
-    void setBasisState(std::size_t index) { PLB200_ABI(plb200_sv_set_basis_state_index(h_, static_cast<int64_t>(index))); }
+    void setBasisState(std::size_t index) {
+        queue_ = detail::OpsBlob{};
+        PLB200_ABI(plb200_sv_set_basis_state_index(h_, static_cast<int64_t>(index)));
+    }
     void setStateVector(const ComplexT *state, std::size_t state_size, const std::vector<std::size_t> &wires,
                         bool = false) {
         PLB200_ABORT_IF_NOT(state_size == (std::size_t{1} << wires.size()), "Inconsistent state and wires dimensions.");
+        queue_ = detail::OpsBlob{};
         const auto w = detail::to_i64(wires);
         const auto v = detail::to_c128(state, state_size);
         PLB200_ABI(plb200_sv_set_state_vector(h_, v.data(), w.data(), static_cast<int64_t>(w.size())));
@@ -239,23 +294,35 @@ template <class Precision = double> class StateVectorB200 {
     }
     void setStateVector(const std::vector<std::size_t> &indices, const std::vector<ComplexT> &values) {
         PLB200_ABORT_IF(indices.size() != values.size(), "Indices and values length must match");
+        queue_ = detail::OpsBlob{};
         const auto i = detail::to_i64(indices);
         const auto v = detail::to_c128(values.data(), values.size());
         PLB200_ABI(plb200_sv_set_state_indices(h_, i.data(), v.data(), static_cast<int64_t>(i.size())));
     }
-    void updateData(const StateVectorB200 &other) { PLB200_ABI(plb200_sv_d2d(h_, other.h_)); }
+    void updateData(const StateVectorB200 &other) {
+        queue_ = detail::OpsBlob{};
+        PLB200_ABI(plb200_sv_d2d(h_, other.handle()));
+    }
     void updateData(const ComplexT *host, std::size_t length) { CopyHostDataToGpu(host, length, false); }
     void updateData(const std::vector<ComplexT> &host) { CopyHostDataToGpu(host.data(), host.size(), false); }
-    void collapse(std::size_t wire, bool branch) { PLB200_ABI(plb200_sv_collapse(h_, static_cast<int64_t>(wire), branch)); }
-    void normalize() { PLB200_ABI(plb200_sv_normalize(h_)); }
+    void collapse(std::size_t wire, bool branch) {
+        flush();
+        PLB200_ABI(plb200_sv_collapse(h_, static_cast<int64_t>(wire), branch));
+    }
+    void normalize() {
+        flush();
+        PLB200_ABI(plb200_sv_normalize(h_));
+    }
 
     // ---- copies (StateVectorCudaBase.hpp) --------------------------------------------------
     void CopyHostDataToGpu(const ComplexT *host, std::size_t length, bool async = false) {
         PLB200_ABORT_IF_NOT(length == getLength(), "Sizes do not match for Host and GPU data");
+        queue_ = detail::OpsBlob{};
         PLB200_ABI(plb200_sv_h2d(h_, host, static_cast<int64_t>(length), async));
     }
     void CopyGpuDataToHost(ComplexT *host, std::size_t length, bool async = false) const {
         PLB200_ABORT_IF_NOT(length == getLength(), "Sizes do not match for Host and GPU data");
+        flush();
         PLB200_ABI(plb200_sv_d2h(h_, host, static_cast<int64_t>(length), async));
     }
     void CopyGpuDataToGpuIn(const StateVectorB200 &other, bool = false) { updateData(other); }
@@ -264,7 +331,10 @@ template <class Precision = double> class StateVectorB200 {
         CopyGpuDataToHost(v.data(), v.size());
         return v;
     }
-    [[nodiscard]] std::int64_t kernelLaunches() const { return plb200_sv_kernel_launches(h_); }
+    [[nodiscard]] std::int64_t kernelLaunches() const {
+        flush();
+        return plb200_sv_kernel_launches(h_);
+    }
 
     static bool isNativeGate(const std::string &name) {
         static const char *names[] = {"Identity", "PauliX", "PauliY", "PauliZ", "Hadamard", "S", "SX", "T", "PhaseShift",
@@ -286,9 +356,16 @@ template <class Precision = double> class StateVectorB200 {
         while ((std::size_t{1} << n) < length) n++;
         return n;
     }
+    static bool lazy_default() {
+        const char *e = std::getenv("PLB200_LAZY");
+        return !(e && e[0] == '0');
+    }
+    static constexpr std::size_t kMaxQueue = 1 << 16;
     plb200_sv *h_ = nullptr;
     std::size_t num_qubits_;
     DevTag<int> dev_tag_;
+    bool lazy_ = lazy_default();
+    mutable detail::OpsBlob queue_;
 };
 
 } // namespace Pennylane::LightningB200
