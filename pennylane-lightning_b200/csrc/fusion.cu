@@ -543,11 +543,11 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     if ((ro & cm_l) == (cv_l & rmask_l)) umask |= 1u << u;
                     if (__builtin_popcount(ro & pm_l) & 1) upar |= 1u << u;
                 }
-                t.umask = static_cast<uint16_t>(umask), t.upar = static_cast<uint16_t>(upar);
+                t.umask = umask, t.upar = upar;
                 const bool one_ctrl_reg = __builtin_popcount(cm_reg) == 1 && (cv_l & cm_reg) == cm_reg;
                 const int creg = cm_reg ? reg_of_local(__builtin_ctz(cm_reg)) : 0;
                 if (it.overlap) {
-                    t.slot = static_cast<uint16_t>(st.slots.size());
+                    t.slot = static_cast<uint32_t>(st.slots.size());
                     st.slots.push_back(it.slot);
                     st.slot_scale.push_back(std::norm(sigma));
                     if (it.pw.x) {
@@ -568,6 +568,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     if (pf.pre_swap) { // pivot: X first, same controls
                         TileOp<T2> x = t;
                         x.code = make_code(swap_kind, p, swap_kind == K_SWAP_CR ? creg : 0);
+                        if (x.cm_tid | x.cmask_o) x.code |= F_COND;
                         top[op_cursor++] = x;
                     }
                     int kind = pf.kind, c = 0;
@@ -591,8 +592,14 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     t.m[0] = mk<T2>(d0.real(), d0.imag());
                     t.m[1] = mk<T2>(d1.real(), d1.imag());
                 }
+                if (t.cm_tid | t.cmask_o) t.code |= F_COND;
+                if (t.pm_tid | t.pmask_o) t.code |= F_PAR;
+                {
+                    const int kd = code_kind(t.code);
+                    if (kd == K_DIAG1_R || kd == K_DIAG1_T) t.m[0] = t.m[1]; // the one phase, in the prefetched slot
+                }
 #if defined(PLB200_HOST_EMU)
-                g_kind_hist[(t.code >> 4) & 31]++;
+                g_kind_hist[code_kind(t.code)]++;
 #endif
                 top[op_cursor++] = t;
             }

@@ -35,18 +35,20 @@ namespace tile {
 #define PLB_POPCLL(x) __builtin_popcountll(x)
 #endif
 
-constexpr int kMaxR = 4;
-constexpr int kMaxPassOps = 224;
+constexpr int kMaxR = 5;
+constexpr int kMaxPassOps = 208;
 constexpr int kMaxPassRounds = 22;
 constexpr int kMaxThreadBits = 9;
 
-// forward pass: one state, 2^12 (c128) / 2^13 (c64) amplitudes = 64 KiB per tile, 16 per thread
+// forward pass: one state, 2^12 (c128) / 2^13 (c64) amplitudes = 64 KiB per tile; 16 (c128) / 32 (c64)
+// amplitudes per thread = 64 data registers either way (measured: c128 with R = 5 needs 255 registers,
+// 8 warps/SM, and loses to R = 4 at 16 warps/SM although it executes 25 % fewer instructions)
 template <typename T2> struct FwdCfg;
 template <> struct FwdCfg<double2> {
     static constexpr int M = 12, LOW = 3, R = 4, NS = 1, MINB = 2;
 };
 template <> struct FwdCfg<float2> {
-    static constexpr int M = 13, LOW = 4, R = 4, NS = 1, MINB = 2;
+    static constexpr int M = 13, LOW = 4, R = 5, NS = 1, MINB = 2;
 };
 // adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
 template <typename T2> struct AdjCfg;
@@ -93,16 +95,37 @@ enum : int {
     K_FIRST_DIAG = K_DIAG_R,
     K_FIRST_OVL = K_OVL_X,
 };
-PLB_HD constexpr uint32_t make_code(int kind, int p, int c) {
-    return static_cast<uint32_t>(kind) << 4 | static_cast<uint32_t>(p) << 2 | static_cast<uint32_t>(c);
+// Code word of an op: bits 0-7 = dense case index of apply_gate's switch (one jump table), bits 8-12 =
+// kind, bits 13-15 = P, bits 16-18 = C, then flags.
+constexpr uint32_t F_COND = 1u << 20; // has controls (outside / thread bits): needs the predicate
+constexpr uint32_t F_PAR = 1u << 21;  // phase depends on a thread / outside parity
+constexpr uint32_t F_OVL = 1u << 22;  // adjoint overlap op
+PLB_HD constexpr int kind_cases(int kind) {
+    return (kind == K_DIAG_PP || kind == K_SWAP_CR || kind == K_DIAG_CR) ? kMaxR * (kMaxR - 1)
+           : (kind == K_DIAG_T || kind == K_DIAG1_T || kind == K_DIAG_G) ? 1
+                                                                        : kMaxR;
 }
+PLB_HD constexpr int kind_base(int kind) {
+    int b = 0;
+    for (int k = 0; k < kind; k++) b += kind_cases(k);
+    return b;
+}
+PLB_HD constexpr int pc_index(int p, int c) { return p * (kMaxR - 1) + (c < p ? c : c - 1); }
+PLB_HD constexpr uint32_t make_code(int kind, int p, int c) {
+    const int n = kind_cases(kind);
+    const int sub = n == kMaxR * (kMaxR - 1) ? pc_index(p, c) : n == kMaxR ? p : 0;
+    return static_cast<uint32_t>(kind_base(kind) + sub) | static_cast<uint32_t>(kind) << 8 |
+           static_cast<uint32_t>(p) << 13 | static_cast<uint32_t>(c) << 16 | (kind >= K_FIRST_OVL ? F_OVL : 0u);
+}
+PLB_HD constexpr int code_kind(uint32_t code) { return static_cast<int>((code >> 8) & 31u); }
+PLB_HD constexpr int code_p(uint32_t code) { return static_cast<int>((code >> 13) & 7u); }
 
 template <typename T2> struct alignas(16) TileOp {
     uint32_t code;
     uint32_t cm_tid, cv_tid; // controls on thread bits, as masks over threadIdx bits
     uint32_t pm_tid;         // parity mask over threadIdx bits
-    uint16_t umask, upar;    // generic masked forms: bit u = register u is active / has odd parity
-    uint16_t slot, pad;      // adjoint: accumulator slot inside the pass
+    uint32_t umask, upar;    // generic masked forms: bit u = register u is active / has odd parity
+    uint32_t slot;           // adjoint: accumulator slot inside the pass
     uint64_t cmask_o, cval_o, pmask_o; // bits outside the tile: uniform per tile
     T2 m[4];
 };
@@ -122,7 +145,7 @@ struct alignas(16) PassHdr {
 template <typename T2> struct alignas(16) PassParams {
     PassHdr hdr;
     RoundHdr rounds[kMaxPassRounds];
-    TileOp<T2> ops[kMaxPassOps];
+    TileOp<T2> ops[kMaxPassOps + 1]; // +1: the interpreter prefetches op k+1
 };
 
 // ---- shared-memory swizzle.  Amplitude j of the tile lives at element j ^ g(j), where g is a
@@ -185,8 +208,7 @@ PLB_HD void xswap(float &a, float &b) {
 }
 
 template <typename T2, int R, int P, int KIND, bool MASKED>
-PLB_HD void pair_op(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t active) {
-    const T2 m0 = op.m[0];
+PLB_HD void pair_op(T2 (&v)[1 << R], const TileOp<T2> &op, const T2 m0, uint32_t active) {
     T2 m1 = m0, m2 = m0, m3 = m0;
     if constexpr (KIND == K_LU_R || KIND == K_LU_C) m1 = op.m[1];
     if constexpr (KIND == K_LU_C) m2 = op.m[2], m3 = op.m[3];
@@ -257,56 +279,58 @@ template <typename T2, int R, int P, int C> PLB_HD void diag_pp(T2 (&v)[1 << R],
     for (int u = 0; u < (1 << R); u++) cmul_ip(v[u], (((u >> P) ^ (u >> C)) & 1) ? dB : dA);
 }
 
-#define PLB_CASE(KIND, PV, CV, STMT)                                                                     \
-    case ((KIND) << 4 | (PV) << 2 | (CV)): {                                                             \
-        constexpr int P = ((PV) < R ? (PV) : R - 1);                                                     \
-        constexpr int C = ((CV) < R ? (CV) : R - 1);                                                     \
+#define PLB_CASE(IDX, PV, CV, STMT)                                                                      \
+    case (IDX): {                                                                                        \
+        constexpr int P = (PV), C = (CV);                                                                \
         (void)P, (void)C;                                                                                \
         STMT;                                                                                            \
     } break;
-#define PLB_CASES_P(KIND, STMT)                                                                          \
-    PLB_CASE(KIND, 0, 0, STMT) PLB_CASE(KIND, 1, 0, STMT) PLB_CASE(KIND, 2, 0, STMT) PLB_CASE(KIND, 3, 0, STMT)
-#define PLB_CASES_PC(KIND, STMT)                                                                         \
-    PLB_CASE(KIND, 0, 1, STMT) PLB_CASE(KIND, 0, 2, STMT) PLB_CASE(KIND, 0, 3, STMT)                     \
-    PLB_CASE(KIND, 1, 0, STMT) PLB_CASE(KIND, 1, 2, STMT) PLB_CASE(KIND, 1, 3, STMT)                     \
-    PLB_CASE(KIND, 2, 0, STMT) PLB_CASE(KIND, 2, 1, STMT) PLB_CASE(KIND, 2, 3, STMT)                     \
-    PLB_CASE(KIND, 3, 0, STMT) PLB_CASE(KIND, 3, 1, STMT) PLB_CASE(KIND, 3, 2, STMT)
+// case lists per number of register bits: only the register positions that exist are instantiated
+#define PLB_CASES_P_3(KIND, STMT) PLB_CASE(kind_base(KIND) + 0, 0, 0, STMT) PLB_CASE(kind_base(KIND) + 1, 1, 0, STMT) PLB_CASE(kind_base(KIND) + 2, 2, 0, STMT)
+#define PLB_CASES_PC_3(KIND, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 1), 0, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 2), 0, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 0), 1, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 2), 1, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 0), 2, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 1), 2, 1, STMT)
+#define PLB_CASES_P_4(KIND, STMT) PLB_CASE(kind_base(KIND) + 0, 0, 0, STMT) PLB_CASE(kind_base(KIND) + 1, 1, 0, STMT) PLB_CASE(kind_base(KIND) + 2, 2, 0, STMT) PLB_CASE(kind_base(KIND) + 3, 3, 0, STMT)
+#define PLB_CASES_PC_4(KIND, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 1), 0, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 2), 0, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 3), 0, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 0), 1, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 2), 1, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 3), 1, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 0), 2, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 1), 2, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 3), 2, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 0), 3, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 1), 3, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 2), 3, 2, STMT)
+#define PLB_CASES_P_5(KIND, STMT) PLB_CASE(kind_base(KIND) + 0, 0, 0, STMT) PLB_CASE(kind_base(KIND) + 1, 1, 0, STMT) PLB_CASE(kind_base(KIND) + 2, 2, 0, STMT) PLB_CASE(kind_base(KIND) + 3, 3, 0, STMT) PLB_CASE(kind_base(KIND) + 4, 4, 0, STMT)
+#define PLB_CASES_PC_5(KIND, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 1), 0, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 2), 0, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 3), 0, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(0, 4), 0, 4, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 0), 1, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 2), 1, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 3), 1, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(1, 4), 1, 4, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 0), 2, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 1), 2, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 3), 2, 3, STMT) PLB_CASE(kind_base(KIND) + pc_index(2, 4), 2, 4, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 0), 3, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 1), 3, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 2), 3, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(3, 4), 3, 4, STMT) PLB_CASE(kind_base(KIND) + pc_index(4, 0), 4, 0, STMT) PLB_CASE(kind_base(KIND) + pc_index(4, 1), 4, 1, STMT) PLB_CASE(kind_base(KIND) + pc_index(4, 2), 4, 2, STMT) PLB_CASE(kind_base(KIND) + pc_index(4, 3), 4, 3, STMT)
 
-// One gate op on one register set.  thr_ok: the thread-bit controls hold.  pt: parity of the
+// One gate op on one register set.  m0 = op.m[0] (prefetched by the caller).  pt: parity of the
 // thread + outside bits under the op's parity mask.
-template <typename T2, int R>
-PLB_HD void apply_gate(T2 (&v)[1 << R], const TileOp<T2> &op, uint32_t code, bool thr_ok, bool pt) {
-    if (!thr_ok) return;
-    switch (code) {
-        PLB_CASES_P(K_LIFT_R, (pair_op<T2, R, P, K_LIFT_R, false>(v, op, 0u)))
-        PLB_CASES_P(K_LIFT_I, (pair_op<T2, R, P, K_LIFT_I, false>(v, op, 0u)))
-        PLB_CASES_P(K_HAD, (pair_op<T2, R, P, K_HAD, false>(v, op, 0u)))
-        PLB_CASES_P(K_LU_R, (pair_op<T2, R, P, K_LU_R, false>(v, op, 0u)))
-        PLB_CASES_P(K_LU_C, (pair_op<T2, R, P, K_LU_C, false>(v, op, 0u)))
-        PLB_CASES_P(K_SWAP, (pair_op<T2, R, P, K_SWAP, false>(v, op, 0u)))
-        PLB_CASES_P(K_LIFT_R_M, (pair_op<T2, R, P, K_LIFT_R, true>(v, op, op.umask)))
-        PLB_CASES_P(K_LIFT_I_M, (pair_op<T2, R, P, K_LIFT_I, true>(v, op, op.umask)))
-        PLB_CASES_P(K_LU_R_M, (pair_op<T2, R, P, K_LU_R, true>(v, op, op.umask)))
-        PLB_CASES_P(K_LU_C_M, (pair_op<T2, R, P, K_LU_C, true>(v, op, op.umask)))
-        PLB_CASES_P(K_SWAP_M, (pair_op<T2, R, P, K_SWAP, true>(v, op, op.umask)))
-        PLB_CASES_P(K_DIAG_R, (diag_bit<T2, R, P, false, -1>(v, pt ? op.m[1] : op.m[0], pt ? op.m[0] : op.m[1])))
-        PLB_CASES_P(K_DIAG1_R, (diag_bit<T2, R, P, true, -1>(v, op.m[1], op.m[1])))
-        PLB_CASE(K_DIAG_T, 0, 0, (diag_all<T2, R, -1>(v, pt ? op.m[1] : op.m[0])))
-        PLB_CASE(K_DIAG1_T, 0, 0, (pt ? diag_all<T2, R, -1>(v, op.m[1]) : (void)0))
-        PLB_CASES_PC(K_DIAG_PP, (diag_pp<T2, R, P, C>(v, pt ? op.m[1] : op.m[0], pt ? op.m[0] : op.m[1])))
-        PLB_CASES_PC(K_SWAP_CR, (swap_cr<T2, R, P, C>(v)))
-        PLB_CASES_PC(K_DIAG_CR, (diag_bit<T2, R, P, false, C>(v, pt ? op.m[1] : op.m[0], pt ? op.m[0] : op.m[1])))
-        PLB_CASES_P(K_DIAG_CT, (diag_all<T2, R, P>(v, pt ? op.m[1] : op.m[0])))
-    default: { // K_DIAG_G
-        const uint32_t pb = pt ? ~static_cast<uint32_t>(op.upar) : static_cast<uint32_t>(op.upar);
-        const uint32_t active = op.umask;
-        const T2 d0 = op.m[0], d1 = op.m[1];
-#pragma unroll
-        for (int u = 0; u < (1 << R); u++)
-            if (active & (1u << u)) cmul_ip(v[u], (pb >> u & 1) ? d1 : d0);
-    } break;
+#define PLB_DEFINE_APPLY_GATE(RV, CASES_P, CASES_PC)                                                     \
+    template <typename T2>                                                                               \
+    PLB_HD void apply_gate(T2 (&v)[1 << RV], const TileOp<T2> &op, uint32_t code, const T2 m0, bool pt) { \
+        constexpr int R = RV;                                                                            \
+        switch (code & 255u) {                                                                           \
+            CASES_P(K_LIFT_R, (pair_op<T2, R, P, K_LIFT_R, false>(v, op, m0, 0u)))                       \
+            CASES_P(K_LIFT_I, (pair_op<T2, R, P, K_LIFT_I, false>(v, op, m0, 0u)))                       \
+            CASES_P(K_HAD, (pair_op<T2, R, P, K_HAD, false>(v, op, m0, 0u)))                             \
+            CASES_P(K_LU_R, (pair_op<T2, R, P, K_LU_R, false>(v, op, m0, 0u)))                           \
+            CASES_P(K_LU_C, (pair_op<T2, R, P, K_LU_C, false>(v, op, m0, 0u)))                           \
+            CASES_P(K_SWAP, (pair_op<T2, R, P, K_SWAP, false>(v, op, m0, 0u)))                           \
+            CASES_P(K_LIFT_R_M, (pair_op<T2, R, P, K_LIFT_R, true>(v, op, m0, op.umask)))                \
+            CASES_P(K_LIFT_I_M, (pair_op<T2, R, P, K_LIFT_I, true>(v, op, m0, op.umask)))                \
+            CASES_P(K_LU_R_M, (pair_op<T2, R, P, K_LU_R, true>(v, op, m0, op.umask)))                    \
+            CASES_P(K_LU_C_M, (pair_op<T2, R, P, K_LU_C, true>(v, op, m0, op.umask)))                    \
+            CASES_P(K_SWAP_M, (pair_op<T2, R, P, K_SWAP, true>(v, op, m0, op.umask)))                    \
+            CASES_P(K_DIAG_R, (diag_bit<T2, R, P, false, -1>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1])))  \
+            CASES_P(K_DIAG1_R, (diag_bit<T2, R, P, true, -1>(v, m0, m0)))                                \
+            PLB_CASE(kind_base(K_DIAG_T), 0, 0, (diag_all<T2, R, -1>(v, pt ? op.m[1] : m0)))             \
+            PLB_CASE(kind_base(K_DIAG1_T), 0, 0, (pt ? diag_all<T2, R, -1>(v, m0) : (void)0))            \
+            CASES_PC(K_DIAG_PP, (diag_pp<T2, R, P, C>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1])))         \
+            CASES_PC(K_SWAP_CR, (swap_cr<T2, R, P, C>(v)))                                               \
+            CASES_PC(K_DIAG_CR, (diag_bit<T2, R, P, false, C>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1]))) \
+            CASES_P(K_DIAG_CT, (diag_all<T2, R, P>(v, pt ? op.m[1] : m0)))                               \
+        default: { /* K_DIAG_G */                                                                        \
+            const uint32_t pb = pt ? ~op.upar : op.upar;                                                 \
+            const uint32_t active = op.umask;                                                            \
+            const T2 d1 = op.m[1];                                                                       \
+            _Pragma("unroll") for (int u = 0; u < (1 << R); u++) if (active & (1u << u))                 \
+                cmul_ip(v[u], (pb >> u & 1) ? d1 : m0);                                                  \
+        } break;                                                                                         \
+        }                                                                                                \
     }
-}
+PLB_DEFINE_APPLY_GATE(3, PLB_CASES_P_3, PLB_CASES_PC_3)
+PLB_DEFINE_APPLY_GATE(4, PLB_CASES_P_4, PLB_CASES_PC_4)
+PLB_DEFINE_APPLY_GATE(5, PLB_CASES_P_5, PLB_CASES_PC_5)
 
 // Im(conj(a) b), Re(conj(a) b)
 template <typename T2> PLB_HD double im_cb(T2 a, T2 b) {
@@ -335,7 +359,7 @@ template <typename T2, int R>
 PLB_HD double overlap_op(const T2 (&l)[1 << R], const T2 (&h)[1 << R], const TileOp<T2> &op, uint32_t code,
                          bool thr_ok, bool pt) {
     const uint32_t active = thr_ok ? static_cast<uint32_t>(op.umask) : 0u;
-    const int kind = static_cast<int>(code >> 4), p = static_cast<int>((code >> 2) & 3u);
+    const int kind = code_kind(code), p = code_p(code);
     double s = 0;
     if (kind == K_OVL_D) {
         const uint32_t pb = pt ? ~static_cast<uint32_t>(op.upar) : static_cast<uint32_t>(op.upar);
@@ -356,8 +380,12 @@ PLB_HD double overlap_op(const T2 (&l)[1 << R], const T2 (&h)[1 << R], const Til
         constexpr int P = R > 2 ? 2 : R - 1;
         s = isy ? overlap_pair<T2, R, P, true>(l, h, active) : overlap_pair<T2, R, P, false>(l, h, active);
     } break;
-    default: {
+    case 3: {
         constexpr int P = R > 3 ? 3 : R - 1;
+        s = isy ? overlap_pair<T2, R, P, true>(l, h, active) : overlap_pair<T2, R, P, false>(l, h, active);
+    } break;
+    default: {
+        constexpr int P = R > 4 ? 4 : R - 1;
         s = isy ? overlap_pair<T2, R, P, true>(l, h, active) : overlap_pair<T2, R, P, false>(l, h, active);
     } break;
     }
@@ -417,23 +445,32 @@ template <typename T2, class Cfg> struct Exec {
 #pragma unroll
             for (int u = 0; u < NV; u++) h[u] = *reinterpret_cast<const T2 *>(smem1 + (sb ^ rh.sroff[u]));
         }
-        const int k_end = rh.first_op + rh.nops;
-        for (int k = rh.first_op; k < k_end; k++) {
-            const TileOp<T2> &op = pp.ops[k];
-            if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
-            const uint32_t code = op.code;
-            const bool thr_ok = (tid & op.cm_tid) == op.cv_tid;
-            bool pt = false;
-            if (code >= make_code(K_FIRST_DIAG, 0, 0))
-                pt = ((PLB_POPC(tid & op.pm_tid) + PLB_POPCLL(base & op.pmask_o)) & 1) != 0;
+        // software-pipelined decode: the code word and first parameter pair of op k+1 are fetched
+        // from the constant bank while op k executes (ops[] has one slack entry)
+        const TileOp<T2> *ops = pp.ops + rh.first_op;
+        const int nops = rh.nops;
+        uint32_t code = ops[0].code;
+        T2 m0 = ops[0].m[0];
+        for (int k = 0; k < nops; k++) {
+            const TileOp<T2> &op = ops[k];
+            const uint32_t ccode = code;
+            const T2 cm0 = m0;
+            code = ops[k + 1].code;
+            m0 = ops[k + 1].m[0];
+            bool thr_ok = true, pt = false;
+            if (ccode & F_COND) {
+                if ((base & op.cmask_o) != op.cval_o) continue; // uniform per tile
+                thr_ok = (tid & op.cm_tid) == op.cv_tid;
+            }
+            if (ccode & F_PAR) pt = ((PLB_POPC(tid & op.pm_tid) + PLB_POPCLL(base & op.pmask_o)) & 1) != 0;
             if constexpr (NS == 2) {
-                if (code >= make_code(K_FIRST_OVL, 0, 0)) {
-                    reduce(static_cast<int>(op.slot), overlap_op<T2, R>(v, h, op, code, thr_ok, pt));
+                if (ccode & F_OVL) {
+                    reduce(static_cast<int>(op.slot), overlap_op<T2, R>(v, h, op, ccode, thr_ok, pt));
                     continue;
                 }
-                apply_gate<T2, R>(h, op, code, thr_ok, pt);
+                if (thr_ok) apply_gate<T2>(h, op, ccode, cm0, pt);
             }
-            apply_gate<T2, R>(v, op, code, thr_ok, pt);
+            if (thr_ok) apply_gate<T2>(v, op, ccode, cm0, pt);
         }
 #pragma unroll
         for (int u = 0; u < NV; u++) *reinterpret_cast<T2 *>(smem0 + (sb ^ rh.sroff[u])) = v[u];
