@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libplb200.so")
+LIB_PATH = os.environ.get("PLB200_LIB_PATH") or os.path.join(_HERE, "lib", "libplb200.so")
 
 _lib = None
 

@@ -40,15 +40,23 @@ constexpr int kMaxPassOps = 208;
 constexpr int kMaxPassRounds = 22;
 constexpr int kMaxThreadBits = 9;
 
-// forward pass: one state, 2^12 (c128) / 2^13 (c64) amplitudes = 64 KiB per tile; 16 (c128) / 32 (c64)
-// amplitudes per thread = 64 data registers either way (measured: c128 with R = 5 needs 255 registers,
-// 8 warps/SM, and loses to R = 4 at 16 warps/SM although it executes 25 % fewer instructions)
+// forward pass: one state; 16 (c128) / 32 (c64) amplitudes per thread = 64 data registers either way
+// (measured: c128 with R = 5 needs 255 registers, 8 warps/SM, and loses to R = 4 at 16 warps/SM although
+// it executes 25 % fewer instructions).  c128 tiles are 2^11 amplitudes = 32 KiB on 128 threads, four
+// CTAs per SM: measured 4 % faster than 2^12 / 256 threads / two CTAs although it needs 24 instead of
+// 21 passes for the 30-qubit benchmark tape (smaller barriers, memory phases of four CTAs overlap).
 template <typename T2> struct FwdCfg;
+#ifndef PLB200_FWD128_M
+#define PLB200_FWD128_M 11
+#endif
 template <> struct FwdCfg<double2> {
-    static constexpr int M = 12, LOW = 3, R = 4, NS = 1, MINB = 2;
+    static constexpr int M = PLB200_FWD128_M, LOW = 3, R = 4, NS = 1, MINB = 512 >> (M - R); // 128 registers
 };
+#ifndef PLB200_FWD64_M
+#define PLB200_FWD64_M 13
+#endif
 template <> struct FwdCfg<float2> {
-    static constexpr int M = 13, LOW = 4, R = 5, NS = 1, MINB = 2;
+    static constexpr int M = PLB200_FWD64_M, LOW = 4, R = 5, NS = 1, MINB = 512 >> (M - R);
 };
 // adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
 template <typename T2> struct AdjCfg;
