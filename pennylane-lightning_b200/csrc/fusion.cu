@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "tile_exec.cuh"
@@ -45,11 +47,11 @@ struct WarpReduce {
     }
 };
 
-template <typename T2, class Cfg>
+template <typename T2, class Cfg, bool EXT>
 __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
     tile_kernel(T2 *__restrict__ sv0, T2 *__restrict__ sv1, const uint64_t *__restrict__ goff_g,
                 double *__restrict__ acc_g, const __grid_constant__ PassParams<T2> pp) {
-    using E = Exec<T2, Cfg>;
+    using E = Exec<T2, Cfg, EXT>;
     constexpr int M = Cfg::M, LOW = Cfg::LOW, NS = Cfg::NS, NT = E::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *tile0 = smem_raw;
@@ -93,9 +95,9 @@ struct HostReduce {
     double *acc;
     __host__ __device__ void operator()(int slot, double s) const { acc[slot] += s; }
 };
-template <typename T2, class Cfg>
+template <typename T2, class Cfg, bool EXT>
 void emulate_pass(T2 *sv0, T2 *sv1, const uint64_t *goff, double *acc, const PassParams<T2> &pp) {
-    using E = Exec<T2, Cfg>;
+    using E = Exec<T2, Cfg, EXT>;
     std::vector<unsigned char> t0(sizeof(T2) << Cfg::M), t1(sizeof(T2) << Cfg::M);
     const HostReduce red{acc};
     for (uint64_t t = 0; t < pp.hdr.ntiles; t++) {
@@ -132,6 +134,14 @@ bool well_conditioned(const cd *m) {
     return std::abs(m[0] * m[3] - m[1] * m[2]) > 1e-6 * nrm;
 }
 
+// SWAP of two index bits: one (01, 10) block [[0, 1], [1, 0]]
+bool is_swap2(const COp &op) {
+    if (op.kind != OP_PAIRS || op.parity || op.tbits.size() != 2 || op.blocks.size() != 1) return false;
+    const Block2 &b = op.blocks[0];
+    return ((b.a == 1 && b.b == 2) || (b.a == 2 && b.b == 1)) && b.m[0] == cd(0.0) && b.m[3] == cd(0.0) &&
+           b.m[1] == cd(1.0) && b.m[2] == cd(1.0);
+}
+
 FOp classify(const COp &op) {
     FOp f;
     uint64_t t = 0;
@@ -140,6 +150,9 @@ FOp classify(const COp &op) {
     if (op.kind == OP_PROJECT) f.all = ~uint64_t{0};
     if (op.kind == OP_PAIRS && !op.parity && op.tbits.size() == 1 && op.blocks.size() == 1 && op.blocks[0].a == 0 &&
         op.blocks[0].b == 1 && well_conditioned(op.blocks[0].m)) {
+        f.fusable = true;
+        f.nd = t;
+    } else if (is_swap2(op)) {
         f.fusable = true;
         f.nd = t;
     } else if (op.kind == OP_DIAG) {
@@ -241,6 +254,7 @@ struct Step {
     size_t params = 0; // index into the params vector
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
+    bool ext = false; // needs the extended kernel (two-bit SWAPs / tail ladders)
     std::vector<int> slots;          // adjoint: global accumulator slot of each pass-local slot
     std::vector<double> slot_scale;  // ... and the |pending scalar|^2 its overlap was taken under
 };
@@ -310,6 +324,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     std::vector<PassParams<T2>> &params) {
     constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NTB = M - R, SB = Swz<T2>::B;
     constexpr bool is_double = sizeof(T2) == 16;
+    constexpr size_t kMinLadder = 6; // shorter runs are cheaper as ordinary ops in the lean kernel
     const double sig_lo = is_double ? 0x1p-200 : 0x1p-20, sig_hi = is_double ? 0x1p200 : 0x1p20;
     steps.clear();
     arena.clear();
@@ -332,7 +347,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
     size_t first = 0;
     const size_t window = 512;
     const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
-    const size_t max_pass_ops = kMaxPassOps - kMaxPassRounds - 2; // emitted ops; room for the scalar ops
+    const size_t max_pass_ops = kMaxPassOps - kMaxPassRounds - 2 - 24; // emitted ops; room for scalar ops + ladder headers
     std::vector<int> pending, exec;
     cd sigma{1.0, 0.0};
     int last_pass_step = -1;
@@ -499,7 +514,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 return o;
             };
 
-            for (int idx : hp.rounds[r]) {
+            auto emit_item = [&](int idx) {
                 const AdjItem &it = items[idx];
                 const FOp &fo = f[idx];
                 TileOp<T2> t;
@@ -513,7 +528,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     if (pmask == 0) { // one scalar d0 == d1 on the control subspace
                         if (cmask == 0 && allow_scaled) {
                             sigma *= d0; // global phase: nothing to do on the device
-                            continue;
+                            return;
                         }
                         // turn one value-1 control into the parity bit: diag(1, d) on it
                         const uint64_t ones = cmask & cval;
@@ -556,6 +571,9 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                         t.code = make_code(K_OVL_D, 0, 0);
                         t.m[0] = mk<T2>(1.0, it.pw.z ? -1.0 : 1.0);
                     }
+                } else if (is_swap2(it.op)) {
+                    st.ext = true;
+                    t.code = make_code(cm_reg ? K_SWAP2_M : K_SWAP2, reg_pos(it.op.tbits[0]), reg_pos(it.op.tbits[1]));
                 } else if (it.op.kind == OP_PAIRS) {
                     const int p = reg_pos(it.op.tbits[0]);
                     const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0);
@@ -602,7 +620,58 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 g_kind_hist[code_kind(t.code)]++;
 #endif
                 top[op_cursor++] = t;
+            };
+
+            // ---- emission.  Controlled phases "multiply by e^{i phi} where every bit of S is 1" whose S
+            // holds at most one register bit P (the rest on thread / outside bits) are not emitted in
+            // place: they are parked in a bucket per P (P = R: no register bit).  Such an op commutes
+            // with everything else in the round except a later non-diagonal op on its register bit P;
+            // when one arrives the bucket is flushed in place as ordinary ops.  What is still parked at
+            // the end of the round becomes the round's TAIL: buckets of >= 2 entries as one ladder each
+            // (header + entries: one scalar per thread, one multiply), single ones as ordinary ops.
+            struct LEntry {
+                int idx;
+                uint64_t S;
+                cd phase, fold;
+            };
+            auto ladder_entry = [&](int idx, LEntry &e) {
+                const AdjItem &it = items[idx];
+                const FOp &fo = f[idx];
+                if (it.overlap || it.op.kind != OP_DIAG) return false;
+                e.idx = idx, e.fold = cd(1.0);
+                if (fo.pmask == 0) {
+                    if (it.op.cmask == 0 || it.op.cval != it.op.cmask) return false;
+                    e.S = it.op.cmask, e.phase = fo.d[0];
+                } else {
+                    if (__builtin_popcountll(fo.pmask) != 1 || it.op.cmask != 0 || !allow_scaled) return false;
+                    e.S = fo.pmask, e.fold = fo.d[0], e.phase = fo.d[1] / fo.d[0];
+                }
+                return __builtin_popcount(to_local(e.S & T) & rmask_l) <= 1;
+            };
+            std::vector<LEntry> bucket[kMaxR + 1];
+            auto flush_bucket = [&](int bk) {
+                for (const LEntry &e : bucket[bk]) emit_item(e.idx);
+                bucket[bk].clear();
+            };
+            for (int idx : hp.rounds[r]) {
+                const AdjItem &it = items[idx];
+                LEntry e;
+                if (ladder_entry(idx, e)) {
+                    const uint32_t sreg = to_local(e.S & T) & rmask_l;
+                    bucket[sreg ? reg_of_local(__builtin_ctz(sreg)) : R].push_back(e);
+                    continue;
+                }
+                // non-diagonal action on register bits: parked phases on those bits must come first
+                uint64_t ndbits = 0;
+                if (it.overlap) ndbits = it.pw.x;
+                else if (it.op.kind == OP_PAIRS)
+                    for (int b : it.op.tbits) ndbits |= uint64_t{1} << b;
+                for (int i = 0; i < R; i++)
+                    if (ndbits >> hp.tbits[rl[i]] & 1) flush_bucket(i);
+                emit_item(idx);
             }
+            for (int bk = 0; bk <= R; bk++)
+                if (bucket[bk].size() < kMinLadder) flush_bucket(bk);
             const bool last_round = r + 1 == hp.rounds.size();
             const double mag = std::abs(sigma);
             if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && Cfg::NS == 2))) {
@@ -610,6 +679,29 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 sigma = cd(1.0);
             }
             rh[r].nops = op_cursor - rh[r].first_op;
+            for (int bk = 0; bk <= R; bk++) {
+                if (bucket[bk].empty()) continue;
+                st.ext = true;
+                TileOp<T2> hd;
+                std::memset(&hd, 0, sizeof(hd));
+                hd.code = make_code(K_LADDER, bk, 0);
+                hd.slot = static_cast<uint32_t>(bucket[bk].size());
+#if defined(PLB200_HOST_EMU)
+                g_kind_hist[K_LADDER]++;
+#endif
+                top[op_cursor++] = hd;
+                for (const LEntry &e : bucket[bk]) {
+                    TileOp<T2> en;
+                    std::memset(&en, 0, sizeof(en));
+                    en.cm_tid = en.cv_tid = to_tid(to_local(e.S & T) & ~rmask_l);
+                    en.cmask_o = en.cval_o = e.S & ~T;
+                    en.m[0] = mk<T2>(e.phase.real(), e.phase.imag());
+                    sigma *= e.fold;
+                    top[op_cursor++] = en;
+                }
+            }
+            rh[r].nlad = op_cursor - rh[r].first_op - rh[r].nops;
+            if (op_cursor > kMaxPassOps) fail("fusion: pass description overflow");
         }
         hdr->nops_total = op_cursor;
         hdr->nslots = static_cast<int>(st.slots.size());
@@ -625,8 +717,12 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         if (last_pass_step < 0) fail("fusion: pending scalar without a tile pass");
         PassParams<T2> &pp = params[steps[last_pass_step].params];
         RoundHdr &rr = pp.rounds[pp.hdr.nrounds - 1];
-        pp.ops[pp.hdr.nops_total++] = scale_op(sigma);
+        // (a regular op: it goes in front of the round's tail ladders)
+        TileOp<T2> *at = pp.ops + rr.first_op + rr.nops;
+        std::memmove(at + 1, at, sizeof(TileOp<T2>) * static_cast<size_t>(rr.nlad));
+        *at = scale_op(sigma);
         rr.nops++;
+        pp.hdr.nops_total++;
     }
 }
 
@@ -650,10 +746,21 @@ bool scaled_forms_enabled() {
 template <typename T2, class Cfg> void prepare_kernel() {
     static bool done = false;
     if (done) return;
-    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem_bytes_for<Cfg, T2>())));
-    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes_for<Cfg, T2>())));
+    PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     done = true;
+}
+template <typename T2, class Cfg>
+void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, const uint64_t *goff, double *acc,
+                 const PassParams<T2> &pp) {
+    const unsigned nt = 1u << (Cfg::M - Cfg::R);
+    if (st.ext) tile_kernel<T2, Cfg, true><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, goff, acc, pp);
+    else tile_kernel<T2, Cfg, false><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, goff, acc, pp);
+    PLB_CUDA(cudaGetLastError());
 }
 
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
@@ -671,16 +778,41 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, sv.stream));
         PLB_CUDA(cudaStreamSynchronize(sv.stream)); // arena is a local
     }
+    // PLB200_FUSE_TRACE=1: per-step device time on stderr (profiling aid; serialises the steps)
+    const bool trace = std::getenv("PLB200_FUSE_TRACE") != nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (trace) {
+        PLB_CUDA(cudaEventCreate(&ev0));
+        PLB_CUDA(cudaEventCreate(&ev1));
+    }
     for (const Step &st : steps) {
+        if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
         if (st.op >= 0) {
             launch_op(sv, ops[st.op]);
-            continue;
+        } else {
+            launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr,
+                                 reinterpret_cast<const uint64_t *>(dplan + st.off), nullptr, params[st.params]);
+            sv.launches++;
         }
-        tile_kernel<T2, Cfg><<<st.grid, 1 << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream>>>(
-            static_cast<T2 *>(sv.data), nullptr, reinterpret_cast<const uint64_t *>(dplan + st.off), nullptr,
-            params[st.params]);
-        PLB_CUDA(cudaGetLastError());
-        sv.launches++;
+        if (trace) {
+            PLB_CUDA(cudaEventRecord(ev1, sv.stream));
+            PLB_CUDA(cudaEventSynchronize(ev1));
+            float ms = 0;
+            PLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            if (st.op >= 0) std::fprintf(stderr, "[plb200 trace] stand-alone op %d: %.3f ms\n", st.op, ms);
+            else {
+                const PassParams<T2> &pp = params[st.params];
+                std::fprintf(stderr, "[plb200 trace] tile pass: %d items, %d records, %d rounds, tile bits", st.nops,
+                             pp.hdr.nops_total, pp.hdr.nrounds);
+                for (int i = 0; i < pp.hdr.tile_ins.n; i++)
+                    std::fprintf(stderr, " %d", 63 - __builtin_clzll(pp.hdr.tile_ins.lowmask[i] + 1));
+                std::fprintf(stderr, ": %.3f ms\n", ms);
+            }
+        }
+    }
+    if (trace) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
     }
 }
 
@@ -725,10 +857,9 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
             stats[1]++;
             continue;
         }
-        tile_kernel<T2, Cfg><<<st.grid, 1 << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), lambda.stream>>>(
-            static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data),
-            reinterpret_cast<const uint64_t *>(dplan + st.off), dacc + pass_idx * kMaxPassOps, params[st.params]);
-        PLB_CUDA(cudaGetLastError());
+        launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data),
+                             reinterpret_cast<const uint64_t *>(dplan + st.off), dacc + pass_idx * kMaxPassOps,
+                             params[st.params]);
         lambda.launches++;
         pass_idx++;
         stats[0]++;
@@ -841,8 +972,12 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
             continue;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        emulate_pass<T2, Cfg>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off), acc.data(),
-                              params[st.params]);
+        if (st.ext)
+            emulate_pass<T2, Cfg, true>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off), acc.data(),
+                                        params[st.params]);
+        else
+            emulate_pass<T2, Cfg, false>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off),
+                                         acc.data(), params[st.params]);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
     }
