@@ -70,6 +70,15 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
 
     for (uint64_t t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
         const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
+        // pull the NEXT tile of this CTA from HBM into L2 while this one is processed (one prefetch
+        // per 128-byte line): no registers or shared memory held, the later load hits L2
+        if (t + gridDim.x < pp.hdr.ntiles) {
+            const uint64_t nbase = insert_bits(t + gridDim.x, pp.hdr.tile_ins);
+            for (int l = tid; l < (1 << (M - LOW)); l += NT) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv0 + (nbase | goff[l])));
+                if constexpr (NS == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(sv1 + (nbase | goff[l])));
+            }
+        }
         E::load_tile(tid, base, goff, sv0, tile0);
         if constexpr (NS == 2) E::load_tile(tid, base, goff, sv1, tile1);
         __syncthreads();
@@ -689,16 +698,19 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
 #if defined(PLB200_HOST_EMU)
                 g_kind_hist[K_LADDER]++;
 #endif
-                top[op_cursor++] = hd;
+                top[op_cursor] = hd;
+                const int nrec = ladder_records<T2>(static_cast<int>(bucket[bk].size()));
+                if (op_cursor + nrec > kMaxPassOps) fail("fusion: pass description overflow");
+                std::memset(static_cast<void *>(top + op_cursor + 1), 0, sizeof(TileOp<T2>) * static_cast<size_t>(nrec - 1));
+                LadderEntry<T2> *ens = reinterpret_cast<LadderEntry<T2> *>(top + op_cursor + 1);
                 for (const LEntry &e : bucket[bk]) {
-                    TileOp<T2> en;
-                    std::memset(&en, 0, sizeof(en));
-                    en.cm_tid = en.cv_tid = to_tid(to_local(e.S & T) & ~rmask_l);
-                    en.cmask_o = en.cval_o = e.S & ~T;
-                    en.m[0] = mk<T2>(e.phase.real(), e.phase.imag());
+                    ens->cmask_o = e.S & ~T;
+                    ens->cm_tid = to_tid(to_local(e.S & T) & ~rmask_l);
+                    ens->ph = mk<T2>(e.phase.real(), e.phase.imag());
+                    ens++;
                     sigma *= e.fold;
-                    top[op_cursor++] = en;
                 }
+                op_cursor += nrec;
             }
             rh[r].nlad = op_cursor - rh[r].first_op - rh[r].nops;
             if (op_cursor > kMaxPassOps) fail("fusion: pass description overflow");

@@ -148,6 +148,19 @@ template <typename T2> struct alignas(16) TileOp {
     uint64_t cmask_o, cval_o, pmask_o; // bits outside the tile: uniform per tile
     T2 m[4];
 };
+// Entry of a tail ladder, packed 4 (c128) / 3 (c64) to a TileOp-sized record: the phase applies where
+// every bit of cmask_o (outside the tile) and of cm_tid (thread bits) is 1.
+template <typename T2> struct alignas(16) LadderEntry {
+    uint64_t cmask_o;
+    uint32_t cm_tid, pad;
+    T2 ph;
+};
+template <typename T2> PLB_HD constexpr int ladder_entries_per_record() {
+    return static_cast<int>(sizeof(TileOp<T2>) / sizeof(LadderEntry<T2>));
+}
+template <typename T2> PLB_HD constexpr int ladder_records(int n) {
+    return 1 + (n + ladder_entries_per_record<T2>() - 1) / ladder_entries_per_record<T2>();
+}
 struct alignas(16) RoundHdr {
     int first_op, nops; // regular ops [first_op, first_op + nops), then nlad records of tail ladders
     int nlad, pad;
@@ -538,15 +551,18 @@ template <typename T2, class Cfg, bool EXT> struct Exec {
                 T2 t;
                 t.x = 1, t.y = 0;
                 bool any = false;
-#pragma unroll 1
-                for (int e = 1; e <= n; e++) {
-                    const TileOp<T2> &en = lad[q + e];
-                    if ((base & en.cmask_o) == en.cval_o && (tid & en.cm_tid) == en.cv_tid) {
-                        cmul_ip(t, en.m[0]);
+                const LadderEntry<T2> *en = reinterpret_cast<const LadderEntry<T2> *>(lad + q + 1);
+#pragma unroll 4
+                for (int e = 0; e < n; e++) {
+                    const uint64_t co = en[e].cmask_o;
+                    if ((base & co) != co) continue; // uniform per tile
+                    const uint32_t ct = en[e].cm_tid;
+                    if ((tid & ct) == ct) {
+                        cmul_ip(t, en[e].ph);
                         any = true;
                     }
                 }
-                q += n + 1;
+                q += ladder_records<T2>(n);
                 if (!any) continue;
                 if constexpr (NS == 2) ladder_apply(h, p, t);
                 ladder_apply(v, p, t);
