@@ -216,6 +216,29 @@ __global__ void __launch_bounds__(kThreads)
     block_reduce_store<2>(v, partials + 2 * (static_cast<size_t>(blockIdx.x) * gridDim.y + blockIdx.y));
 }
 
+// <psi| Z-word |psi> for up to W diagonal words in ONE read of the state:
+// sum_i |a_i|^2 (-1)^{popcount(i & z_q)}, q < W  (expval of PauliZ on every wire, ZZ terms of an Ising
+// Hamiltonian, ...).  partials laid out [block][W].
+template <typename T2, int W>
+__global__ void __launch_bounds__(kThreads)
+    zwords_kernel(const T2 *__restrict__ a, uint64_t len, const WordDev *__restrict__ words, int nw, double *partials) {
+    __shared__ uint64_t zs[W];
+    if (threadIdx.x < W) zs[threadIdx.x] = threadIdx.x < nw ? words[threadIdx.x].z : 0;
+    __syncthreads();
+    uint64_t z[W];
+    double v[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) z[q] = zs[q], v[q] = 0;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const T2 x = a[i];
+        const double p = static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+#pragma unroll
+        for (int q = 0; q < W; q++) v[q] += (__popcll(i & z[q]) & 1) ? -p : p;
+    }
+    block_reduce_store<W>(v, partials + static_cast<size_t>(blockIdx.x) * W);
+}
+
 template <typename T2>
 __global__ void __launch_bounds__(kThreads)
     pauli_sum_apply_kernel(T2 *__restrict__ out, const T2 *__restrict__ in, uint64_t len,
@@ -509,6 +532,33 @@ void pauli_inner(StateVec &a, const StateVec &b, const PauliWordMask *words, int
     PLB_CHECK(a.n == b.n && a.precision == b.precision, "pauli_inner: incompatible state vectors");
     if (n_words == 0) return;
     a.set_device();
+    // expectation values of diagonal (Z-only) words: 8 words per read of the state
+    bool all_diag = a.data == b.data;
+    for (int64_t k = 0; k < n_words && all_diag; k++)
+        all_diag = words[k].x == 0 && words[k].cmask == 0 && words[k].ny == 0;
+    if (all_diag && n_words > 1) {
+        constexpr int W = 8;
+        const int nb = reduce_blocks(a, a.length());
+        for (int64_t w0 = 0; w0 < n_words; w0 += W) {
+            const int nw = static_cast<int>(std::min<int64_t>(W, n_words - w0));
+            auto h = to_dev_words(words + w0, nw);
+            WordDev *dw = static_cast<WordDev *>(a.table_buf(h.size() * sizeof(WordDev)));
+            PLB_CUDA(cudaMemcpyAsync(dw, h.data(), h.size() * sizeof(WordDev), cudaMemcpyHostToDevice, a.stream));
+            PLB_CUDA(cudaStreamSynchronize(a.stream));
+            double *part = a.reduce_buf(static_cast<size_t>(W) * nb + W + 8);
+            DISPATCH(a,
+                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), dw,
+                                                                        nw, part)),
+                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), dw,
+                                                                        nw, part)));
+            a.launches++;
+            PLB_CUDA(cudaGetLastError());
+            double r[W];
+            finish_reduce<W>(a, part, 1, nb, r);
+            for (int q = 0; q < nw; q++) out[2 * (w0 + q)] = r[q], out[2 * (w0 + q) + 1] = 0.0;
+        }
+        return;
+    }
     const int64_t kMaxBatch = 4096;
     for (int64_t w0 = 0; w0 < n_words; w0 += kMaxBatch) {
         const int64_t W = std::min(kMaxBatch, n_words - w0);

@@ -115,6 +115,21 @@ def test_pauli_words_fused(plb, ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_diagonal_words_single_pass(plb, ref, dtype):
+    """Z-only words take the one-read kernel (8 words per sweep): <Z_w> for every wire, ZZ / ZZZ words,
+    19 words = two full batches + a ragged one."""
+    n = 11
+    a, b = _pair(plb, ref, n, dtype, 17)
+    words = ["Z"] * n + ["ZZ"] * 5 + ["ZZZ"] * 3
+    wires = [[w] for w in range(n)] + [[w, (w + 3) % n] for w in range(5)] + [[w, w + 2, w + 5] for w in range(3)]
+    each = a.expval_pauli_words_each(words, wires)
+    tol = 10 * TOL[np.dtype(dtype)]
+    for k, (word, ws) in enumerate(zip(words, wires)):
+        term = circuits.hamiltonian_observable(ref, [1.0], [word], [ws], dtype=dtype)
+        assert abs(each[k] - b.expval(term)) < tol, (k, word, ws)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_state_preparation(plb, ref, dtype):
     n = 6
     tol = TOL[np.dtype(dtype)]
