@@ -596,6 +596,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                         TileOp<T2> x = t;
                         x.code = make_code(swap_kind, p, swap_kind == K_SWAP_CR ? creg : 0);
                         if (x.cm_tid | x.cmask_o) x.code |= F_COND;
+                        if (swap_kind == K_SWAP_M) st.ext = true;
                         top[op_cursor++] = x;
                     }
                     int kind = pf.kind, c = 0;
@@ -623,6 +624,10 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 if (t.pm_tid | t.pmask_o) t.code |= F_PAR;
                 {
                     const int kd = code_kind(t.code);
+                    if (kd == K_LU_R || kd == K_LU_C || kd == K_LIFT_R_M || kd == K_LIFT_I_M || kd == K_LU_R_M ||
+                        kd == K_LU_C_M || kd == K_SWAP_M || kd == K_DIAG_PP || kd == K_DIAG_G || kd == K_SWAP2 ||
+                        kd == K_SWAP2_M)
+                        st.ext = true; // kinds only the extended kernel implements
                     if (kd == K_DIAG1_R || kd == K_DIAG1_T) t.m[0] = t.m[1]; // the one phase, in the prefetched slot
                 }
 #if defined(PLB200_HOST_EMU)

@@ -340,10 +340,13 @@ template <typename T2, int R, int P, int C> PLB_HD void diag_pp(T2 (&v)[1 << R],
 
 // One gate op on one register set.  m0 = op.m[0] (prefetched by the caller).  pt: parity of the
 // thread + outside bits under the op's parity mask.
-// EXT = false: the lean interpreter (no two-bit SWAP cases); EXT = true adds them.  Passes that need
-// neither SWAP2 nor ladders run the lean kernel, whose op loop is ~15 % faster (smaller dispatch tree).
+// EXT = false: the lean interpreter = the op kinds of the common gate sets only (rotations, Hadamard,
+// X / CNOT, phase gates and their singly-controlled forms); EXT = true adds the LU forms of arbitrary
+// 2x2 blocks, the register-masked forms, two-register-bit parities and two-bit SWAPs (and round() adds
+// the tail ladders).  A pass runs the lean kernel unless it holds one of those: its dispatch tree and
+// code are half the size, and its op loop decodes on the uniform datapath.
 #define PLB_NO_CASES(KIND, STMT)
-#define PLB_DEFINE_APPLY_GATE(RV, EXTV, CASES_P, CASES_PC, CASES_EXT)                                    \
+#define PLB_DEFINE_APPLY_GATE(RV, EXTV, CASES_P, CASES_PC, CASES_EXT, CASES_P_EXT)                       \
     template <typename T2>                                                                               \
     PLB_HD void apply_gate(T2 (&v)[1 << RV], const TileOp<T2> &op, uint32_t code, const T2 m0, bool pt,  \
                            std::integral_constant<bool, EXTV>) {                                         \
@@ -352,19 +355,19 @@ template <typename T2, int R, int P, int C> PLB_HD void diag_pp(T2 (&v)[1 << R],
             CASES_P(K_LIFT_R, (pair_op<T2, R, P, K_LIFT_R, false>(v, op, m0, 0u)))                       \
             CASES_P(K_LIFT_I, (pair_op<T2, R, P, K_LIFT_I, false>(v, op, m0, 0u)))                       \
             CASES_P(K_HAD, (pair_op<T2, R, P, K_HAD, false>(v, op, m0, 0u)))                             \
-            CASES_P(K_LU_R, (pair_op<T2, R, P, K_LU_R, false>(v, op, m0, 0u)))                           \
-            CASES_P(K_LU_C, (pair_op<T2, R, P, K_LU_C, false>(v, op, m0, 0u)))                           \
+            CASES_P_EXT(K_LU_R, (pair_op<T2, R, P, K_LU_R, false>(v, op, m0, 0u)))                           \
+            CASES_P_EXT(K_LU_C, (pair_op<T2, R, P, K_LU_C, false>(v, op, m0, 0u)))                           \
             CASES_P(K_SWAP, (pair_op<T2, R, P, K_SWAP, false>(v, op, m0, 0u)))                           \
-            CASES_P(K_LIFT_R_M, (pair_op<T2, R, P, K_LIFT_R, true>(v, op, m0, op.umask)))                \
-            CASES_P(K_LIFT_I_M, (pair_op<T2, R, P, K_LIFT_I, true>(v, op, m0, op.umask)))                \
-            CASES_P(K_LU_R_M, (pair_op<T2, R, P, K_LU_R, true>(v, op, m0, op.umask)))                    \
-            CASES_P(K_LU_C_M, (pair_op<T2, R, P, K_LU_C, true>(v, op, m0, op.umask)))                    \
-            CASES_P(K_SWAP_M, (pair_op<T2, R, P, K_SWAP, true>(v, op, m0, op.umask)))                    \
+            CASES_P_EXT(K_LIFT_R_M, (pair_op<T2, R, P, K_LIFT_R, true>(v, op, m0, op.umask)))                \
+            CASES_P_EXT(K_LIFT_I_M, (pair_op<T2, R, P, K_LIFT_I, true>(v, op, m0, op.umask)))                \
+            CASES_P_EXT(K_LU_R_M, (pair_op<T2, R, P, K_LU_R, true>(v, op, m0, op.umask)))                    \
+            CASES_P_EXT(K_LU_C_M, (pair_op<T2, R, P, K_LU_C, true>(v, op, m0, op.umask)))                    \
+            CASES_P_EXT(K_SWAP_M, (pair_op<T2, R, P, K_SWAP, true>(v, op, m0, op.umask)))                    \
             CASES_P(K_DIAG_R, (diag_bit<T2, R, P, false, -1>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1])))  \
             CASES_P(K_DIAG1_R, (diag_bit<T2, R, P, true, -1>(v, m0, m0)))                                \
             PLB_CASE(kind_base(K_DIAG_T), 0, 0, (diag_all<T2, R, -1>(v, pt ? op.m[1] : m0)))             \
             PLB_CASE(kind_base(K_DIAG1_T), 0, 0, (pt ? diag_all<T2, R, -1>(v, m0) : (void)0))            \
-            CASES_PC(K_DIAG_PP, (diag_pp<T2, R, P, C>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1])))         \
+            CASES_EXT(K_DIAG_PP, (diag_pp<T2, R, P, C>(v, pt ? op.m[1] : m0, pt ? m0 : op.m[1])))         \
             CASES_PC(K_SWAP_CR, (swap_cr<T2, R, P, C>(v)))                                               \
             CASES_EXT(K_SWAP2, (swap2<T2, R, P, C, false>(v, 0u)))                                       \
             CASES_EXT(K_SWAP2_M, (swap2<T2, R, P, C, true>(v, op.umask)))                                \
@@ -379,12 +382,12 @@ template <typename T2, int R, int P, int C> PLB_HD void diag_pp(T2 (&v)[1 << R],
         } break;                                                                                         \
         }                                                                                                \
     }
-PLB_DEFINE_APPLY_GATE(3, false, PLB_CASES_P_3, PLB_CASES_PC_3, PLB_NO_CASES)
-PLB_DEFINE_APPLY_GATE(4, false, PLB_CASES_P_4, PLB_CASES_PC_4, PLB_NO_CASES)
-PLB_DEFINE_APPLY_GATE(5, false, PLB_CASES_P_5, PLB_CASES_PC_5, PLB_NO_CASES)
-PLB_DEFINE_APPLY_GATE(3, true, PLB_CASES_P_3, PLB_CASES_PC_3, PLB_CASES_PC_3)
-PLB_DEFINE_APPLY_GATE(4, true, PLB_CASES_P_4, PLB_CASES_PC_4, PLB_CASES_PC_4)
-PLB_DEFINE_APPLY_GATE(5, true, PLB_CASES_P_5, PLB_CASES_PC_5, PLB_CASES_PC_5)
+PLB_DEFINE_APPLY_GATE(3, false, PLB_CASES_P_3, PLB_CASES_PC_3, PLB_NO_CASES, PLB_NO_CASES)
+PLB_DEFINE_APPLY_GATE(4, false, PLB_CASES_P_4, PLB_CASES_PC_4, PLB_NO_CASES, PLB_NO_CASES)
+PLB_DEFINE_APPLY_GATE(5, false, PLB_CASES_P_5, PLB_CASES_PC_5, PLB_NO_CASES, PLB_NO_CASES)
+PLB_DEFINE_APPLY_GATE(3, true, PLB_CASES_P_3, PLB_CASES_PC_3, PLB_CASES_PC_3, PLB_CASES_P_3)
+PLB_DEFINE_APPLY_GATE(4, true, PLB_CASES_P_4, PLB_CASES_PC_4, PLB_CASES_PC_4, PLB_CASES_P_4)
+PLB_DEFINE_APPLY_GATE(5, true, PLB_CASES_P_5, PLB_CASES_PC_5, PLB_CASES_PC_5, PLB_CASES_P_5)
 
 // Im(conj(a) b), Re(conj(a) b)
 template <typename T2> PLB_HD double im_cb(T2 a, T2 b) {
