@@ -295,8 +295,14 @@ def run_ours(args):
                         "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
                         "launches_per_step": passes, "avg_launch_ms": ms_per_step / max(1, passes),
                         "avg_algorithmic_bytes_per_launch": alg_total / max(1, passes),
-                        "note": "achieved = effective HBM GB/s: bytes the same gates move un-fused / time; the "
-                                "pass itself is FP64-issue bound, its real DRAM rate is traffic/avg_launch",
+                        "dram_GBps": (traffic / (ms_per_step / max(1, passes) * 1e-3) / 1e9) if traffic else None,
+                        "dram_frac_of_peak": (traffic / (ms_per_step / max(1, passes) * 1e-3) / 1e9 / peak)
+                        if traffic else None,
+                        "note": "achieved = effective HBM GB/s = algorithmic bytes of the gates a launch applies "
+                                "(SURVEY 8d: what they move one sweep per gate) / launch time; it exceeds the HBM "
+                                "peak because a fused pass applies ~37 gates per sweep. The pass itself is bound "
+                                "by instruction issue (ncu: issue 57 %, FP64 pipe 31 %), its real DRAM rate is "
+                                "dram_GBps = traffic / avg_launch",
                         "per_gate_kernels": per_gate}
         else:
             dom = max(fam_ms, key=fam_ms.get)

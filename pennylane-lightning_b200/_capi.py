@@ -25,7 +25,7 @@ class B200Error(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compile libplb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8", "all", "emu"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("building libplb200.so failed:\n" + res.stdout + res.stderr)

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 
 #include "tile_exec.cuh"
 
@@ -49,8 +50,8 @@ struct WarpReduce {
 
 template <typename T2, class Cfg, bool EXT>
 __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
-    tile_kernel(T2 *__restrict__ sv0, T2 *__restrict__ sv1, const uint64_t *__restrict__ goff_g,
-                double *__restrict__ acc_g, const __grid_constant__ PassParams<T2> pp) {
+    tile_kernel(T2 *__restrict__ sv0, T2 *__restrict__ sv1, double *__restrict__ acc_g,
+                const __grid_constant__ PassParams<T2> pp) {
     using E = Exec<T2, Cfg, EXT>;
     constexpr int M = Cfg::M, LOW = Cfg::LOW, NS = Cfg::NS, NT = E::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -60,7 +61,8 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
     double *acc = reinterpret_cast<double *>(goff + (1 << (M - LOW)));
     static_assert(sizeof(PassParams<T2>) <= 32764, "kernel parameter space");
 
-    for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = goff_g[i];
+    // global offset of every 2^LOW-amplitude line of a tile, from the tile's bit positions
+    for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = tile_line_offset<M, LOW>(pp.hdr, i);
     if constexpr (NS == 2)
         for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT) acc[i] = 0.0;
     __syncthreads();
@@ -105,8 +107,12 @@ struct HostReduce {
     __host__ __device__ void operator()(int slot, double s) const { acc[slot] += s; }
 };
 template <typename T2, class Cfg, bool EXT>
-void emulate_pass(T2 *sv0, T2 *sv1, const uint64_t *goff, double *acc, const PassParams<T2> &pp) {
+void emulate_pass(T2 *sv0, T2 *sv1, double *acc, const PassParams<T2> &pp) {
     using E = Exec<T2, Cfg, EXT>;
+    std::vector<uint64_t> goff_v(size_t{1} << (Cfg::M - Cfg::LOW));
+    for (size_t i = 0; i < goff_v.size(); i++)
+        goff_v[i] = tile_line_offset<Cfg::M, Cfg::LOW>(pp.hdr, static_cast<int>(i));
+    const uint64_t *goff = goff_v.data();
     std::vector<unsigned char> t0(sizeof(T2) << Cfg::M), t1(sizeof(T2) << Cfg::M);
     const HostReduce red{acc};
     for (uint64_t t = 0; t < pp.hdr.ntiles; t++) {
@@ -258,9 +264,8 @@ struct HostPass {
 };
 
 struct Step {
-    int op = -1;       // >= 0: stand-alone item
-    size_t off = 0;    // else: offset of the pass's goff table in the arena (bytes)
-    size_t params = 0; // index into the params vector
+    int op = -1;       // >= 0: stand-alone item; -1: tile pass; -2: multiply the state by `scale`
+    cd scale{1.0, 0.0};
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
     bool ext = false; // needs the extended kernel (two-bit SWAPs / tail ladders)
@@ -327,25 +332,25 @@ PairForm pair_form(const cd *min, bool fold) {
 // allow_scaled: uncontrolled rotations / diagonals may leave a scalar factor with the host (sigma),
 // which is multiplied back into the state by a K_DIAG_T op before it can over/underflow, at the end
 // of every adjoint pass, and at the end of the tape.
-template <typename T2, class Cfg>
-void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled,
-                    std::vector<Step> &steps, std::vector<unsigned char> &arena,
-                    std::vector<PassParams<T2>> &params) {
+//
+// Steps are handed to on_step(step, pass description or nullptr) AS THEY ARE PRODUCED, so the caller can
+// launch pass k while pass k+1 is being scheduled (the description is reused: consume it in the call).
+template <typename T2, class Cfg, class OnStep>
+void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled, OnStep &&on_step) {
     constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NTB = M - R, SB = Swz<T2>::B;
     constexpr bool is_double = sizeof(T2) == 16;
     constexpr size_t kMinLadder = 6; // shorter runs are cheaper as ordinary ops in the lean kernel
     const double sig_lo = is_double ? 0x1p-200 : 0x1p-20, sig_hi = is_double ? 0x1p200 : 0x1p20;
-    steps.clear();
-    arena.clear();
-    params.clear();
     if (n < M + 1 || items.size() < 2) {
         for (size_t i = 0; i < items.size(); i++) {
             Step st;
             st.op = static_cast<int>(i);
-            steps.push_back(st);
+            on_step(st, nullptr);
         }
         return;
     }
+    auto cur = std::make_unique<PassParams<T2>>();
+    const bool multistart = (sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr;
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
     std::vector<FOp> f(items.size());
     for (size_t i = 0; i < items.size(); i++) {
@@ -359,7 +364,6 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
     const size_t max_pass_ops = kMaxPassOps - kMaxPassRounds - 2 - 24; // emitted ops; room for scalar ops + ladder headers
     std::vector<int> pending, exec;
     cd sigma{1.0, 0.0};
-    int last_pass_step = -1;
 
     auto scale_op = [](cd s) {
         TileOp<T2> t;
@@ -377,11 +381,25 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             if (!done[i]) pending.push_back(static_cast<int>(i));
         // ---- choose the tile bits
         uint64_t T = grow(f, pending, lowbits, M, full, full, exec);
+        if (multistart) {
+            // greedy growth restarted from every bit some pending op needs: keeps the best tile.
+            // (30q benchmark tape: 24 -> 20 passes for ~2 ms more host time per pass, hidden behind
+            // the previous pass running on the GPU; not worth it for states a pass sweeps in microseconds)
+            uint64_t cand = 0;
+            for (int i : pending) cand |= f[i].nd;
+            cand &= full & ~lowbits;
+            std::vector<int> ex2;
+            for (int b = 0; b < n; b++) {
+                if (!(cand >> b & 1)) continue;
+                const uint64_t Tc = grow(f, pending, lowbits | (uint64_t{1} << b), M, full, full, ex2);
+                if (ex2.size() > exec.size()) exec = ex2, T = Tc;
+            }
+        }
         if (exec.size() < 2) {
             // nothing worth a tile pass: run the first pending item on its own
             Step st;
             st.op = static_cast<int>(first);
-            steps.push_back(st);
+            on_step(st, nullptr);
             done[first] = 1;
             continue;
         }
@@ -427,18 +445,15 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         pass_ops.clear();
         for (const auto &r : hp.rounds) pass_ops.insert(pass_ops.end(), r.begin(), r.end());
         for (int i : pass_ops) done[i] = 1;
+        // the last step of the tape?  (then the carried scalar is multiplied back here)
+        bool tape_done = true;
+        for (size_t i = first; i < items.size() && tape_done; i++) tape_done = done[i] != 0;
 
         // ---- encode the plan
-        const size_t goff_n = size_t{1} << (M - LOW);
-        const size_t bytes = goff_n * sizeof(uint64_t);
-        const size_t off = (arena.size() + 255) & ~size_t{255};
-        arena.resize(off + bytes, 0);
-        params.emplace_back();
-        std::memset(&params.back(), 0, sizeof(PassParams<T2>));
-        PassHdr *hdr = &params.back().hdr;
-        uint64_t *goff = reinterpret_cast<uint64_t *>(arena.data() + off);
-        RoundHdr *rh = params.back().rounds;
-        TileOp<T2> *top = params.back().ops;
+        std::memset(static_cast<void *>(cur.get()), 0, sizeof(PassParams<T2>));
+        PassHdr *hdr = &cur->hdr;
+        RoundHdr *rh = cur->rounds;
+        TileOp<T2> *top = cur->ops;
         hdr->nrounds = static_cast<int>(hp.rounds.size());
         hdr->ntiles = uint64_t{1} << (n - M);
         hdr->tile_ins.n = 0;
@@ -446,12 +461,6 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         int local_of[64];
         for (int i = 0; i < 64; i++) local_of[i] = -1;
         for (int i = 0; i < M; i++) local_of[hp.tbits[i]] = i;
-        for (size_t j = 0; j < goff_n; j++) {
-            uint64_t o = 0;
-            for (int i = LOW; i < M; i++)
-                if ((j >> (i - LOW)) & 1) o |= uint64_t{1} << hp.tbits[i];
-            goff[j] = o;
-        }
         auto to_local = [&](uint64_t mask) {
             uint32_t l = 0;
             for (int i = 0; i < M; i++)
@@ -688,7 +697,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 if (bucket[bk].size() < kMinLadder) flush_bucket(bk);
             const bool last_round = r + 1 == hp.rounds.size();
             const double mag = std::abs(sigma);
-            if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && Cfg::NS == 2))) {
+            if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && (Cfg::NS == 2 || tape_done)))) {
                 top[op_cursor++] = scale_op(sigma);
                 sigma = cd(1.0);
             }
@@ -722,24 +731,15 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         }
         hdr->nops_total = op_cursor;
         hdr->nslots = static_cast<int>(st.slots.size());
-        st.off = off;
-        st.params = params.size() - 1;
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
         st.nrounds = hdr->nrounds, st.nops = static_cast<int>(pass_ops.size());
-        last_pass_step = static_cast<int>(steps.size());
-        steps.push_back(std::move(st));
+        on_step(st, cur.get());
     }
     if (sigma != cd(1.0)) {
-        // a scalar commutes with everything that follows: multiply it back in the last pass
-        if (last_pass_step < 0) fail("fusion: pending scalar without a tile pass");
-        PassParams<T2> &pp = params[steps[last_pass_step].params];
-        RoundHdr &rr = pp.rounds[pp.hdr.nrounds - 1];
-        // (a regular op: it goes in front of the round's tail ladders)
-        TileOp<T2> *at = pp.ops + rr.first_op + rr.nops;
-        std::memmove(at + 1, at, sizeof(TileOp<T2>) * static_cast<size_t>(rr.nlad));
-        *at = scale_op(sigma);
-        rr.nops++;
-        pp.hdr.nops_total++;
+        // stand-alone ops followed the last pass: the carried scalar needs a sweep of its own
+        Step st;
+        st.op = -2, st.scale = sigma;
+        on_step(st, nullptr);
     }
 }
 
@@ -772,29 +772,19 @@ template <typename T2, class Cfg> void prepare_kernel() {
     done = true;
 }
 template <typename T2, class Cfg>
-void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, const uint64_t *goff, double *acc,
-                 const PassParams<T2> &pp) {
+void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, double *acc, const PassParams<T2> &pp) {
     const unsigned nt = 1u << (Cfg::M - Cfg::R);
-    if (st.ext) tile_kernel<T2, Cfg, true><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, goff, acc, pp);
-    else tile_kernel<T2, Cfg, false><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, goff, acc, pp);
+    if (st.ext) tile_kernel<T2, Cfg, true><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, acc, pp);
+    else tile_kernel<T2, Cfg, false><<<st.grid, nt, smem_bytes_for<Cfg, T2>(), stream>>>(sv0, sv1, acc, pp);
     PLB_CUDA(cudaGetLastError());
 }
 
+// Forward tape: every step is launched the moment the scheduler has produced it (the pass description
+// is a by-value kernel parameter), so the host schedules pass k+1 while the GPU runs pass k.
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
     using Cfg = FwdCfg<T2>;
-    std::vector<Step> steps;
-    std::vector<unsigned char> arena;
-    std::vector<PassParams<T2>> params;
     const auto items = as_items(ops);
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), steps, arena, params);
-    // ---- upload every pass's offset table once, then launch the whole schedule back to back
-    unsigned char *dplan = nullptr;
-    if (!arena.empty()) {
-        prepare_kernel<T2, Cfg>();
-        dplan = static_cast<unsigned char *>(sv.plan_buf(arena.size()));
-        PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, sv.stream));
-        PLB_CUDA(cudaStreamSynchronize(sv.stream)); // arena is a local
-    }
+    prepare_kernel<T2, Cfg>();
     // PLB200_FUSE_TRACE=1: per-step device time on stderr (profiling aid; serialises the steps)
     const bool trace = std::getenv("PLB200_FUSE_TRACE") != nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -802,13 +792,13 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         PLB_CUDA(cudaEventCreate(&ev0));
         PLB_CUDA(cudaEventCreate(&ev1));
     }
-    for (const Step &st : steps) {
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) {
         if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
-        if (st.op >= 0) {
-            launch_op(sv, ops[st.op]);
-        } else {
-            launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr,
-                                 reinterpret_cast<const uint64_t *>(dplan + st.off), nullptr, params[st.params]);
+        if (st.op >= 0) launch_op(sv, ops[st.op]);
+        else if (st.op == -2) scale(sv, st.scale);
+        else {
+            launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
         if (trace) {
@@ -816,17 +806,16 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
             PLB_CUDA(cudaEventSynchronize(ev1));
             float ms = 0;
             PLB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-            if (st.op >= 0) std::fprintf(stderr, "[plb200 trace] stand-alone op %d: %.3f ms\n", st.op, ms);
+            if (st.op != -1) std::fprintf(stderr, "[plb200 trace] stand-alone op %d: %.3f ms\n", st.op, ms);
             else {
-                const PassParams<T2> &pp = params[st.params];
-                std::fprintf(stderr, "[plb200 trace] tile pass: %d items, %d records, %d rounds, tile bits", st.nops,
-                             pp.hdr.nops_total, pp.hdr.nrounds);
-                for (int i = 0; i < pp.hdr.tile_ins.n; i++)
-                    std::fprintf(stderr, " %d", 63 - __builtin_clzll(pp.hdr.tile_ins.lowmask[i] + 1));
+                std::fprintf(stderr, "[plb200 trace] tile pass (%s): %d items, %d records, %d rounds, tile bits",
+                             st.ext ? "ext" : "lean", st.nops, pp->hdr.nops_total, pp->hdr.nrounds);
+                for (int i = 0; i < pp->hdr.tile_ins.n; i++)
+                    std::fprintf(stderr, " %d", 63 - __builtin_clzll(pp->hdr.tile_ins.lowmask[i] + 1));
                 std::fprintf(stderr, ": %.3f ms\n", ms);
             }
         }
-    }
+    });
     if (trace) {
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
@@ -837,30 +826,20 @@ template <typename T2>
 void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
                        double *acc_host, int64_t stats[3]) {
     using Cfg = AdjCfg<T2>;
-    std::vector<Step> steps;
-    std::vector<unsigned char> arena;
-    std::vector<PassParams<T2>> params;
-    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), steps, arena,
-                            params);
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
-    // device accumulators: one slab of kMaxPassOps doubles per tile pass
-    size_t n_pass = 0;
-    for (const Step &st : steps)
-        if (st.op < 0) n_pass++;
-    unsigned char *dplan = nullptr;
-    double *dacc = nullptr;
-    const size_t acc_off = (arena.size() + 255) & ~size_t{255};
-    const size_t acc_bytes = n_pass * kMaxPassOps * sizeof(double);
-    if (n_pass) {
-        prepare_kernel<T2, Cfg>();
-        dplan = static_cast<unsigned char *>(lambda.plan_buf(acc_off + acc_bytes));
-        PLB_CUDA(cudaMemcpyAsync(dplan, arena.data(), arena.size(), cudaMemcpyHostToDevice, lambda.stream));
-        dacc = reinterpret_cast<double *>(dplan + acc_off);
-        PLB_CUDA(cudaMemsetAsync(dacc, 0, acc_bytes, lambda.stream));
-        PLB_CUDA(cudaStreamSynchronize(lambda.stream));
-    }
-    size_t pass_idx = 0;
-    for (const Step &st : steps) {
+    prepare_kernel<T2, Cfg>();
+    // device accumulators: one slab of kMaxPassOps doubles per tile pass; a pass executes >= 2 items
+    const size_t max_pass = items.size() / 2 + 1;
+    const size_t acc_bytes = max_pass * kMaxPassOps * sizeof(double);
+    double *dacc = static_cast<double *>(lambda.plan_buf(acc_bytes));
+    PLB_CUDA(cudaMemsetAsync(dacc, 0, acc_bytes, lambda.stream));
+    struct PassSlots {
+        std::vector<int> slots;
+        std::vector<double> scale;
+    };
+    std::vector<PassSlots> passes;
+    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) {
         if (st.op >= 0) {
             const AdjItem &it = items[st.op];
             if (it.overlap) {
@@ -872,27 +851,23 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
                 launch_op(hl, it.op);
             }
             stats[1]++;
-            continue;
+            return;
         }
+        if (st.op == -2) fail("fusion: adjoint passes carry no scalar across passes");
         launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data),
-                             reinterpret_cast<const uint64_t *>(dplan + st.off), dacc + pass_idx * kMaxPassOps,
-                             params[st.params]);
+                             dacc + passes.size() * kMaxPassOps, *pp);
         lambda.launches++;
-        pass_idx++;
+        passes.push_back({st.slots, st.slot_scale});
         stats[0]++;
         stats[2] += st.nops;
-    }
-    if (n_pass) {
-        std::vector<double> h(n_pass * kMaxPassOps);
-        PLB_CUDA(cudaMemcpyAsync(h.data(), dacc, acc_bytes, cudaMemcpyDeviceToHost, lambda.stream));
+    });
+    if (!passes.empty()) {
+        std::vector<double> h(passes.size() * kMaxPassOps);
+        PLB_CUDA(cudaMemcpyAsync(h.data(), dacc, h.size() * sizeof(double), cudaMemcpyDeviceToHost, lambda.stream));
         PLB_CUDA(cudaStreamSynchronize(lambda.stream));
-        pass_idx = 0;
-        for (const Step &st : steps) {
-            if (st.op >= 0) continue;
-            for (size_t s = 0; s < st.slots.size(); s++)
-                acc_host[st.slots[s]] += st.slot_scale[s] * h[pass_idx * kMaxPassOps + s];
-            pass_idx++;
-        }
+        for (size_t pi = 0; pi < passes.size(); pi++)
+            for (size_t s = 0; s < passes[pi].slots.size(); s++)
+                acc_host[passes[pi].slots[s]] += passes[pi].scale[s] * h[pi * kMaxPassOps + s];
     } else
         lambda.sync();
 }
@@ -901,21 +876,14 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
 } // namespace
 
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
-    std::vector<Step> steps;
-    std::vector<unsigned char> arena;
     const auto items = as_items(ops);
-    if (precision == 64) {
-        std::vector<PassParams<double2>> params;
-        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, steps, arena, params);
-    } else {
-        std::vector<PassParams<float2>> params;
-        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, steps, arena, params);
-    }
     out[0] = out[1] = out[2] = out[3] = 0;
-    for (const auto &s : steps) {
+    auto count = [&](const Step &s, const void *) {
         if (s.op >= 0) out[1]++;
-        else out[0]++, out[2] += s.nrounds, out[3] += s.nops;
-    }
+        else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
+    };
+    if (precision == 64) build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, count);
+    else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, count);
 }
 
 bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const std::vector<int64_t> &tp,
@@ -976,29 +944,33 @@ void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
 template <typename T2, class Cfg>
 int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0, T2 *sv1, double *acc_host,
                   int n_slots, int (*standalone)(void *, int), void *ctx, int64_t stats[4]) {
-    std::vector<Step> steps;
-    std::vector<unsigned char> arena;
-    std::vector<PassParams<T2>> params;
-    build_schedule<T2, Cfg>(n, 148, items, scaled, steps, arena, params);
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    for (const Step &st : steps) {
+    int rc = 0;
+    build_schedule<T2, Cfg>(n, 148, items, scaled, [&](const Step &st, const PassParams<T2> *pp) {
+        if (rc) return;
         if (st.op >= 0) {
             stats[1]++;
-            if (standalone(ctx, st.op) != 0) return 1;
-            continue;
+            rc = standalone(ctx, st.op);
+            return;
+        }
+        if (st.op == -2) {
+            for (T2 *sv : {sv0, sv1}) {
+                if (!sv) continue;
+                for (uint64_t i = 0; i < (uint64_t{1} << n); i++) {
+                    const cd v = cd(sv[i].x, sv[i].y) * st.scale;
+                    sv[i] = mk<T2>(v.real(), v.imag());
+                }
+            }
+            return;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if (st.ext)
-            emulate_pass<T2, Cfg, true>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off), acc.data(),
-                                        params[st.params]);
-        else
-            emulate_pass<T2, Cfg, false>(sv0, sv1, reinterpret_cast<const uint64_t *>(arena.data() + st.off),
-                                         acc.data(), params[st.params]);
+        if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
+        else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
-    }
-    return 0;
+    });
+    return rc;
 }
 void emu_kind_hist(int64_t out[32], bool reset) {
     for (int i = 0; i < 32; i++) {

@@ -173,6 +173,14 @@ struct alignas(16) PassHdr {
     int nslots, pad;
     BitInsert tile_ins; // zeros at the M tile bits
 };
+// Global offset of line i (2^LOW amplitudes) of a tile: bit b of i -> tile bit LOW + b.
+template <int M, int LOW> PLB_HD uint64_t tile_line_offset(const PassHdr &h, int i) {
+    uint64_t o = 0;
+#pragma unroll
+    for (int b = LOW; b < M; b++)
+        if ((i >> (b - LOW)) & 1) o |= h.tile_ins.lowmask[b] + 1; // lowmask = (1 << position) - 1
+    return o;
+}
 // The whole pass description travels as a __grid_constant__ kernel parameter (constant bank,
 // uniform loads): nothing about the ops is fetched through the LSU/L1 data path.
 template <typename T2> struct alignas(16) PassParams {

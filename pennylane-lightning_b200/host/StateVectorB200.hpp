@@ -294,7 +294,7 @@ template <class Precision = double> class StateVectorB200 {
     }
     void setStateVector(const std::vector<std::size_t> &indices, const std::vector<ComplexT> &values) {
         PLB200_ABORT_IF(indices.size() != values.size(), "Indices and values length must match");
-        queue_ = detail::OpsBlob{};
+        flush(); // only the listed amplitudes are overwritten: the others must see the pending gates
         const auto i = detail::to_i64(indices);
         const auto v = detail::to_c128(values.data(), values.size());
         PLB200_ABI(plb200_sv_set_state_indices(h_, i.data(), v.data(), static_cast<int64_t>(i.size())));

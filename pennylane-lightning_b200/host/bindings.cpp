@@ -57,6 +57,7 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
         .def("getCurrentGPU", [](const SV &s) { return s.getDevTag().getDeviceID(); })
         .def("GetNumGPUs", [](const SV &) { return DevicePool<int>::getTotalDevices(); })
         .def("kernelLaunches", &SV::kernelLaunches)
+        .def("pendingOps", &SV::pendingOps, "gates queued by the per-gate calls and not yet applied")
         .def("resetStateVector", [](SV &s, bool async) { s.resetStateVector(async); }, py::arg("async") = false)
         .def("setBasisState",
              [](SV &s, const std::vector<std::size_t> &state, const std::vector<std::size_t> &wires, bool async) {

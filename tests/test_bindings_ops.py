@@ -217,3 +217,45 @@ def test_shot_based_api_matches_reference(ref, p):
     assert sum(m.counts(300).values()) == 300
     with pytest.raises(RuntimeError, match="do not support samples"):
         m.sample_obs(cases[-1][0], 10)
+
+
+@pytest.mark.parametrize("p", PREC)
+def test_lazy_gate_queue(p, ref):
+    """Per-gate calls are validated at call time, queued, and applied as one fused tape on the first
+    read: same state as the reference, errors raised where the reference raises them,
+    full-state preparations drop the queue."""
+    SV, M, dt = classes(p)
+    n = 14
+    tape = circuits.random_circuit(n, 4, 5)
+    sv = SV(n)
+    for o in tape:
+        getattr(sv, o["name"])(o["wires"], o["inverse"], o["params"])
+    assert sv.pendingOps() == len(tape)  # nothing has touched the device yet
+    with pytest.raises(Exception):
+        sv.RX([n + 3], False, [0.1])  # invalid wire: raised by the call, not at flush time
+    with pytest.raises(Exception):
+        sv.RX([0], False, [])  # missing parameter
+    assert sv.pendingOps() == len(tape)
+    got = state(sv, dt)  # first read: one fused tape
+    assert sv.pendingOps() == 0
+    r = ref.StateVector(n, dt)
+    r.apply_ops(tape)
+    np.testing.assert_allclose(got, r.get_state(), rtol=0, atol=1e-12 if p == "128" else 1e-5)
+    # measurements flush as well
+    sv.Hadamard([0], False, [])
+    r.apply("Hadamard", [0])
+    m = M(sv)
+    assert sv.pendingOps() == 1
+    pr = np.asarray(m.probs([0, 1]))
+    assert sv.pendingOps() == 0
+    np.testing.assert_allclose(pr, r.probs([0, 1]), atol=1e-12 if p == "128" else 1e-5)
+    # a full-state preparation discards pending gates; applyMatrix keeps program order (flushes first)
+    sv.PauliX([1], False, [])
+    sv.resetStateVector()
+    assert sv.pendingOps() == 0 and np.isclose(state(sv, dt)[0], 1.0)
+    sv.PauliX([n - 1], False, [])  # |0..01>
+    sv.applyMatrix(np.array([[0, 1], [1, 0]], dtype=dt), [n - 2], False)  # |0..11>
+    sv.PauliX([n - 1], False, [])  # |0..10>
+    assert sv.pendingOps() == 1
+    out = state(sv, dt)
+    assert np.isclose(out[2], 1.0) and np.isclose(np.abs(out).sum(), 1.0)
