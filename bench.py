@@ -231,13 +231,16 @@ def run_ours(args):
                      for o in ops)
     barrier()
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         reset()
         if world > 1:
             sv.apply_ops(ops, fuse=fuse)
         else:
             sv.apply_ops(plb.OpsBlob(ops), fuse=fuse)  # marshals the host tape every step
         ez = np.asarray(expvals())
+        e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -346,7 +349,7 @@ def run_ours(args):
                        sv.n_swaps else 0},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tape_bytes,
-                    "d2h_bytes_per_step": 8 * n, "steps": e2e_steps,
+                    "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "step_ms": e2e_step_ms,
                     "what": "reset + applyOperations(host tape) + expval(PauliZ(w)) for every wire -> host"},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
             "checks": {"norm_minus_1": None, "expval_z0": float(ez[0])},

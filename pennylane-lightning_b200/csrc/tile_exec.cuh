@@ -50,22 +50,31 @@ template <typename T2> struct FwdCfg;
 #ifndef PLB200_FWD128_M
 #define PLB200_FWD128_M 11
 #endif
+#ifndef PLB200_FWD128_MINB
+#define PLB200_FWD128_MINB 6 /* 80 registers, 24 warps/SM: measured 283 ms vs 314 (5) vs 319 (4) on the 30q tape */
+#endif
 template <> struct FwdCfg<double2> {
-    static constexpr int M = PLB200_FWD128_M, LOW = 3, R = 4, NS = 1, MINB = 512 >> (M - R); // 128 registers
+    static constexpr int M = PLB200_FWD128_M, LOW = 3, R = 4, NS = 1, MINB = PLB200_FWD128_MINB;
 };
 #ifndef PLB200_FWD64_M
 #define PLB200_FWD64_M 13
 #endif
+#ifndef PLB200_FWD64_MINB
+#define PLB200_FWD64_MINB 3 /* 80 registers, 24 warps/SM: 176 ms vs 207 (2) on the 30q tape */
+#endif
 template <> struct FwdCfg<float2> {
-    static constexpr int M = PLB200_FWD64_M, LOW = 4, R = 5, NS = 1, MINB = 512 >> (M - R);
+    static constexpr int M = PLB200_FWD64_M, LOW = 4, R = 5, NS = 1, MINB = PLB200_FWD64_MINB;
 };
 // adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
 template <typename T2> struct AdjCfg;
+#ifndef PLB200_ADJ_MINB
+#define PLB200_ADJ_MINB 2
+#endif
 template <> struct AdjCfg<double2> {
-    static constexpr int M = 11, LOW = 3, R = 3, NS = 2, MINB = 2;
+    static constexpr int M = 11, LOW = 3, R = 3, NS = 2, MINB = PLB200_ADJ_MINB;
 };
 template <> struct AdjCfg<float2> {
-    static constexpr int M = 12, LOW = 4, R = 3, NS = 2, MINB = 2;
+    static constexpr int M = 12, LOW = 4, R = 3, NS = 2, MINB = 2; // 512 threads: 64 registers
 };
 
 // op kinds; dispatch code = kind << 4 | P << 2 | C.  Every form updates its registers IN PLACE (each
