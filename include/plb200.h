@@ -209,6 +209,13 @@ int plb200_sv_unpack_bit(plb200_sv *sv, int64_t bit, int keep, const void *buf);
  * (cudaDeviceEnablePeerAccess over NVLink); each GPU of the pair calls it with its own keep. */
 int plb200_sv_swap_bit_peer(plb200_sv *sv, int64_t bit, int keep, void *peer_device_ptr,
                             int do_half);
+/* k = 1..3 global bits <-> k local bits in ONE all-to-all exchange over peer memory (NVSwitch): with
+ * my_value = this rank's value on the swapped global bits (bit i of it pairs with bits[i]), the block of
+ * local-bit value p trades places with block my_value of the rank whose global bits read p;
+ * peer_device_ptrs[p] = that rank's mapped slab (entry my_value unused).  Moves (1 - 2^-k) S per GPU
+ * instead of k S/2 (replaces the chained custatevecSVSwapWorker exchanges, MPIWorker.hpp:1-311). */
+int plb200_sv_swap_bits_peer(plb200_sv *sv, const int64_t *bits, int64_t k, int64_t my_value,
+                             void *const *peer_device_ptrs);
 
 /* CUDA IPC plumbing for the peer path (one process per GPU): export the slab of `sv` as a 64-byte
  * handle, map a peer's slab into this process (peer access over NVLink is enabled lazily), unmap. */

@@ -115,5 +115,6 @@ void collapse_zero(StateVec &sv, int bit, int keep_value);
 void pack_bit(const StateVec &sv, int bit, int keep, void *buf);
 void unpack_bit(StateVec &sv, int bit, int keep, const void *buf);
 void swap_bit_peer(StateVec &sv, int bit, int keep, void *peer, int do_half);
+void swap_bits_peer(StateVec &sv, const int *bits, int k, int my_value, void *const *peers);
 
 } // namespace plb200

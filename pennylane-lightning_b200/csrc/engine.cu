@@ -902,6 +902,20 @@ int plb200_sv_swap_bit_peer(plb200_sv *sv, int64_t bit, int keep, void *peer, in
     ABI_CATCH
 }
 
+int plb200_sv_swap_bits_peer(plb200_sv *sv, const int64_t *bits, int64_t k, int64_t my_value,
+                             void *const *peer_device_ptrs) {
+    ABI_TRY
+    PLB_CHECK(k >= 1 && k <= 3, "Invalid number of bits");
+    int b[3];
+    for (int64_t i = 0; i < k; i++) {
+        PLB_CHECK(bits[i] >= 0 && bits[i] < sv->s.n, "Invalid bit");
+        b[i] = static_cast<int>(bits[i]);
+    }
+    PLB_CHECK(my_value >= 0 && my_value < (int64_t{1} << k), "Invalid rank value");
+    swap_bits_peer(sv->s, b, static_cast<int>(k), static_cast<int>(my_value), peer_device_ptrs);
+    ABI_CATCH
+}
+
 int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64) {
     ABI_TRY
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -382,6 +382,50 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// k-bit all-to-all exchange (k global bits <-> k local bits at once): with r = this rank's value on the
+// swapped global bits, the block of local-bit value p (p != r) trades places with block r of the rank
+// whose global bits read p — one in-place transpose over 2^k GPUs that moves (1 - 2^-k) S per GPU
+// instead of k S/2 for k single-bit swaps.  Each pair of ranks splits its block in halves so both
+// directions of every link carry data; grid.y = partner.
+struct MultiSwapArgs {
+    BitInsert ins; // zeros at the k local bit positions
+    uint64_t nrest;
+    int npartners;
+    void *peer[7];
+    uint64_t my_off[7]; // local-bit deposit of the partner's value p
+    uint64_t peer_off;  // local-bit deposit of my value r
+    int lower[7];       // 1: this rank handles the first half of the pair's elements
+};
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    swap_multi_peer_kernel(T2 *__restrict__ mine, const __grid_constant__ MultiSwapArgs a) {
+    constexpr int U = 4;
+    const int pi = blockIdx.y;
+    T2 *__restrict__ peer = static_cast<T2 *>(a.peer[pi]);
+    const uint64_t half = a.nrest >> 1;
+    const uint64_t lo = a.lower[pi] ? 0 : half, hi = a.lower[pi] ? half : a.nrest;
+    const uint64_t my_off = a.my_off[pi], peer_off = a.peer_off;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t g0 = lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < hi; g0 += U * stride) {
+        uint64_t b[U];
+        T2 x[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t g = g0 + u * stride;
+            b[u] = insert_bits(g < hi ? g : g0, a.ins);
+            y[u] = peer[b[u] | peer_off];
+            x[u] = mine[b[u] | my_off];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (g0 + u * stride < hi) {
+                mine[b[u] | my_off] = y[u];
+                peer[b[u] | peer_off] = x[u];
+            }
+        }
+    }
+}
+
 BitInsert single_insert(int bit) {
     BitInsert bi;
     bi.n = 1;
@@ -763,6 +807,43 @@ void swap_bit_peer(StateVec &sv, int bit, int keep, void *peer, int do_half) {
                                                                    lo, hi, ins, my_bit, peer_bit)),
              (swap_peer_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), static_cast<T2 *>(peer),
                                                                    lo, hi, ins, my_bit, peer_bit)));
+    sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void swap_bits_peer(StateVec &sv, const int *bits, int k, int my_value, void *const *peers) {
+    PLB_CHECK(k >= 1 && k <= 3, "swap_bits_peer: 1..3 bits");
+    sv.set_device();
+    MultiSwapArgs a;
+    uint64_t mask = 0;
+    for (int i = 0; i < k; i++) mask |= uint64_t{1} << bits[i];
+    PLB_CHECK(__builtin_popcountll(mask) == k, "swap_bits_peer: bits must be distinct");
+    a.ins.n = 0;
+    for (int b = 0; b < 64; b++)
+        if (mask >> b & 1) a.ins.lowmask[a.ins.n++] = (uint64_t{1} << b) - 1;
+    a.nrest = sv.length() >> k;
+    auto deposit = [&](int v) {
+        uint64_t o = 0;
+        for (int i = 0; i < k; i++)
+            if (v >> i & 1) o |= uint64_t{1} << bits[i];
+        return o;
+    };
+    a.peer_off = deposit(my_value);
+    a.npartners = 0;
+    for (int p = 0; p < (1 << k); p++) {
+        if (p == my_value) continue;
+        PLB_CHECK(peers[p] != nullptr, "swap_bits_peer: missing peer mapping");
+        a.peer[a.npartners] = peers[p];
+        a.my_off[a.npartners] = deposit(p);
+        a.lower[a.npartners] = my_value < p ? 1 : 0;
+        a.npartners++;
+    }
+    const uint64_t half = a.nrest >> 1;
+    const unsigned nbx = static_cast<unsigned>(std::max<uint64_t>(
+        1, std::min<uint64_t>((half + kThreads * 4 - 1) / (kThreads * 4), uint64_t(sv.sm_count) * 32 / a.npartners)));
+    dim3 grid(nbx, static_cast<unsigned>(a.npartners));
+    DISPATCH(sv, (swap_multi_peer_kernel<T2><<<grid, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), a)),
+             (swap_multi_peer_kernel<T2><<<grid, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), a)));
     sv.launches++;
     PLB_CUDA(cudaGetLastError());
 }

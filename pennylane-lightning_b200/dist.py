@@ -125,6 +125,19 @@ class LocalEngine:
         _capi._check(_capi.lib().plb200_sv_swap_bit_peer(self.sv._h, C.c_int64(bit), int(keep),
                                                          C.c_void_p(self.peers[partner]), int(half)))
 
+    def swap_bits_peer(self, bits, my_value, partner_ranks):
+        """all-to-all exchange of len(bits) local bits; partner_ranks[p] = rank holding value p."""
+        import ctypes as C
+
+        from . import _capi
+
+        k = len(bits)
+        arr = (C.c_void_p * (1 << k))()
+        for p, r in enumerate(partner_ranks):
+            arr[p] = None if p == my_value else self.peers[r]
+        b = (C.c_int64 * k)(*bits)
+        _capi._check(_capi.lib().plb200_sv_swap_bits_peer(self.sv._h, b, C.c_int64(k), C.c_int64(my_value), arr))
+
     def sync(self):
         self.sv.sync()
 
@@ -202,7 +215,7 @@ class DistStateVector:
             handles = [None] * self.world
             dist.all_gather_object(handles, self.engine.ipc_handle(), group=group)
             for r in range(self.world):
-                if r != self.rank and bin(r ^ self.rank).count("1") == 1:
+                if r != self.rank:  # every rank: the multi-bit swap is an all-to-all over NVSwitch
                     self.engine.open_peer(r, handles[r])
         self.reset()
 
@@ -305,6 +318,31 @@ class DistStateVector:
         self.n_swaps += 1
         self.swap_bytes += send.numel() * send.element_size()
 
+    def _swap_multi(self, pairs):
+        """Exchange several (global wire, local wire) pairs in ONE all-to-all over peer memory:
+        (1 - 2^-k) S per GPU on the links instead of k S/2 for k chained swaps."""
+        dist = self.dist
+        gbits = [self.phys[gw] for gw, _ in pairs]
+        lbits = [self.phys[lw] for _, lw in pairs]
+        k = len(pairs)
+        my_value = sum(((self.rank >> (gb - self.nloc)) & 1) << i for i, gb in enumerate(gbits))
+        partner_ranks = []
+        for p in range(1 << k):
+            r = self.rank
+            for i, gb in enumerate(gbits):
+                bit = 1 << (gb - self.nloc)
+                r = (r | bit) if (p >> i) & 1 else (r & ~bit)
+            partner_ranks.append(r)
+        self.engine.sync()
+        dist.barrier(group=self.group)
+        self.engine.swap_bits_peer(lbits, my_value, partner_ranks)
+        self.engine.sync()
+        dist.barrier(group=self.group)
+        for (gw, lw), gb, lb in zip(pairs, gbits, lbits):
+            self.phys[gw], self.phys[lw] = lb, gb
+        self.n_swaps += k
+        self.swap_bytes += ((1 << self.nloc) - (1 << (self.nloc - k))) * self.dtype.itemsize
+
     # ------------------------------------------------------------------ tape execution
     def apply_ops(self, ops, fuse=True):
         pending = [normalize_op(o) for o in ops]
@@ -344,8 +382,12 @@ class DistStateVector:
         cand = [w for w in range(self.n) if not self._is_global(w) and w not in need]
         # never evict the three lowest local bits' wires first: high local bits pack in full 128-B lines
         cand.sort(key=lambda w: (nxt.get(w, 1 << 30), self.phys[w]), reverse=True)
-        for gw, lw in zip(need, cand):
-            self._swap(gw, lw)
+        pairs = list(zip(need, cand))
+        if self.swap_mode == "peer" and 1 < len(pairs) <= 3 and hasattr(self.engine, "swap_bits_peer"):
+            self._swap_multi(pairs)
+        else:
+            for gw, lw in pairs:
+                self._swap(gw, lw)
 
     # ------------------------------------------------------------------ measurements
     def _allreduce(self, arr):

@@ -19,7 +19,7 @@ def test_header_declares_the_boundary():
     syms = declared_symbols()
     assert len(syms) >= 45
     for s in ("plb200_sv_apply", "plb200_sv_apply_matrix", "plb200_adjoint_jacobian", "plb200_probs",
-              "plb200_expval_pauli_words", "plb200_generate_samples", "plb200_sv_swap_bit_peer"):
+              "plb200_expval_pauli_words", "plb200_generate_samples", "plb200_sv_swap_bit_peer", "plb200_sv_swap_bits_peer"):
         assert s in syms
 
 
