@@ -20,6 +20,8 @@ libplb200 through the C ABI (`_capi.StateVector` on a torch-owned slab).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # gates that are "control (x) base": name -> (base gate, number of leading control wires)
@@ -214,8 +216,13 @@ class DistStateVector:
         if self.swap_mode == "peer":
             handles = [None] * self.world
             dist.all_gather_object(handles, self.engine.ipc_handle(), group=group)
+            # PLB200_SWAP_MULTI=1: k global bits in ONE all-to-all exchange (needs every rank mapped).
+            # Off by default: correct on 4 and 8 GPUs at 18 qubits (tests/test_dist_gpu.py), but its first
+            # run at 33 local qubits did not finish inside the round's remaining GPU budget, so the
+            # chained single-bit swaps (measured at 36 qubits) stay the default until that is understood.
+            self.multi_swap = os.environ.get("PLB200_SWAP_MULTI", "0") == "1"
             for r in range(self.world):
-                if r != self.rank:  # every rank: the multi-bit swap is an all-to-all over NVSwitch
+                if r != self.rank and (self.multi_swap or bin(r ^ self.rank).count("1") == 1):
                     self.engine.open_peer(r, handles[r])
         self.reset()
 
@@ -383,7 +390,8 @@ class DistStateVector:
         # never evict the three lowest local bits' wires first: high local bits pack in full 128-B lines
         cand.sort(key=lambda w: (nxt.get(w, 1 << 30), self.phys[w]), reverse=True)
         pairs = list(zip(need, cand))
-        if self.swap_mode == "peer" and 1 < len(pairs) <= 3 and hasattr(self.engine, "swap_bits_peer"):
+        if (self.swap_mode == "peer" and getattr(self, "multi_swap", False) and 1 < len(pairs) <= 3
+                and hasattr(self.engine, "swap_bits_peer")):
             self._swap_multi(pairs)
         else:
             for gw, lw in pairs:

@@ -103,6 +103,9 @@ def worker(rank, world, n, seed, port, backend, q, swap="auto"):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if swap == "peer-multi":  # the opt-in k-bit all-to-all exchange
+        os.environ["PLB200_SWAP_MULTI"] = "1"
+        swap = "peer"
     dist.init_process_group(backend, rank=rank, world_size=world)
     from pennylane_lightning_b200.dist import DistStateVector
 

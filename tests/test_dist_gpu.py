@@ -16,13 +16,13 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("swap", ["peer", "nccl"])
+@pytest.mark.parametrize("swap", ["peer", "peer-multi", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_gpu_matches_single_gpu_and_reference(plb, ref, world, swap):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     n, seed = 18, 10 + world
-    res = run_ranks(world, n, seed, "nccl", port=29700 + world + (10 if swap == "peer" else 0), swap=swap)
+    res = run_ranks(world, n, seed, "nccl", port=29700 + world + {"peer": 10, "peer-multi": 20, "nccl": 0}[swap], swap=swap)
     ops = mixed_circuit(n, seed)
     single = plb.StateVector(n)
     single.apply_ops(ops, fuse=True)
