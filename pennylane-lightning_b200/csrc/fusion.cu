@@ -350,7 +350,9 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         return;
     }
     auto cur = std::make_unique<PassParams<T2>>();
-    const bool multistart = (sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr;
+    // PLB200_SCHED_GREEDY1=1 / PLB200_SCHED_MULTISTART=1 force the choice (tests fuzz both on small states)
+    const bool multistart = std::getenv("PLB200_SCHED_MULTISTART") != nullptr ||
+                            ((sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr);
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
     std::vector<FOp> f(items.size());
     for (size_t i = 0; i < items.size(); i++) {

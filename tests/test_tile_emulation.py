@@ -177,3 +177,72 @@ def test_adjoint_sweep_through_tile_interpreter(emu, plb, dtype):
     assert rc == 0, emu.plb200_emu_last_error()
     assert stats[0] >= 1
     np.testing.assert_allclose(jac, np.asarray(expect).ravel(), rtol=0, atol=TOL[np.dtype(dtype)] * 20)
+
+
+def _fuzz_tape(n, rng, m, style):
+    """Random tapes over the whole gate set: mixed (1-/2-/3-qubit gates, multi-controlled gates with
+    random control values, MultiRZ, global phases, angles at multiples of pi/2) or QFT-like ladders."""
+    names1 = ["Hadamard", "PauliX", "PauliY", "PauliZ", "S", "SX", "T", "RX", "RY", "RZ", "PhaseShift", "Rot"]
+    names2 = ["CNOT", "CZ", "CY", "SWAP", "CRX", "CRY", "CRZ", "CRot", "ControlledPhaseShift", "IsingXX", "IsingZZ",
+              "IsingXY", "IsingYY", "SingleExcitation", "SingleExcitationPlus", "SingleExcitationMinus", "PSWAP"]
+    npar = {"RX": 1, "RY": 1, "RZ": 1, "PhaseShift": 1, "Rot": 3, "CRX": 1, "CRY": 1, "CRZ": 1, "CRot": 3,
+            "ControlledPhaseShift": 1, "IsingXX": 1, "IsingZZ": 1, "IsingXY": 1, "IsingYY": 1, "SingleExcitation": 1,
+            "SingleExcitationPlus": 1, "SingleExcitationMinus": 1, "PSWAP": 1}
+    ops = []
+    for _ in range(m):
+        r = rng.random()
+        if style == "ladder":
+            t = int(rng.integers(n))
+            ops.append(circuits.op("Hadamard", [t]))
+            for c in rng.permutation(n)[: int(rng.integers(1, n))]:
+                if int(c) != t:
+                    ops.append(circuits.op("ControlledPhaseShift", [int(c), t], [rng.uniform(0, 6)]))
+            if rng.random() < 0.3:
+                ops.append(circuits.op("SWAP", [int(x) for x in rng.permutation(n)[:2]]))
+        elif r < 0.4:
+            nm = names1[int(rng.integers(len(names1)))]
+            ang = rng.uniform(0, 6, npar.get(nm, 0))
+            if rng.random() < 0.15:
+                ang = np.array([np.pi * int(rng.integers(0, 5)) / 2] * len(ang))
+            ops.append(circuits.op(nm, [int(rng.integers(n))], ang, inverse=bool(rng.integers(2))))
+        elif r < 0.75:
+            nm = names2[int(rng.integers(len(names2)))]
+            ops.append(circuits.op(nm, [int(x) for x in rng.permutation(n)[:2]], rng.uniform(0, 6, npar.get(nm, 0)),
+                                   inverse=bool(rng.integers(2))))
+        elif r < 0.8:
+            ops.append(circuits.op(["Toffoli", "CSWAP"][int(rng.integers(2))], [int(x) for x in rng.permutation(n)[:3]]))
+        elif r < 0.92:
+            k = int(rng.integers(1, 4))
+            p = [int(x) for x in rng.permutation(n)[: k + 2]]
+            nm = ["RY", "RZ", "PauliX", "PhaseShift", "Hadamard", "RX", "SWAP", "IsingZZ", "GlobalPhase"][int(rng.integers(9))]
+            nt = 2 if nm in ("SWAP", "IsingZZ") else 1
+            ops.append(circuits.op(nm, p[:nt], rng.uniform(0, 6, npar.get(nm, 1 if nm == "GlobalPhase" else 0)),
+                                   ctrl_wires=p[nt:nt + k], ctrl_values=[bool(b) for b in rng.integers(0, 2, k)]))
+        elif r < 0.97:
+            k = int(rng.integers(2, 6))
+            ops.append(circuits.op("MultiRZ", [int(x) for x in rng.permutation(n)[:k]], [rng.uniform(0, 6)]))
+        else:
+            ops.append(circuits.op("GlobalPhase", [0], [rng.uniform(0, 6)]))
+    return ops
+
+
+@pytest.mark.parametrize("multistart", [False, True])
+def test_fuzz_random_tapes(emu, plb, multistart, monkeypatch):
+    """30 random tapes per scheduler variant (the multi-start tile choice is normally reserved for
+    states >= 1 GiB; PLB200_SCHED_MULTISTART forces it here)."""
+    if multistart:
+        monkeypatch.setenv("PLB200_SCHED_MULTISTART", "1")
+    else:
+        monkeypatch.setenv("PLB200_SCHED_GREEDY1", "1")
+    for seed in range(30):
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(12, 16))
+        dtype = [np.complex128, np.complex64][seed % 2]
+        style = "ladder" if seed % 5 == 0 else "mixed"
+        m = int(rng.integers(40, 70)) if style == "ladder" else int(rng.integers(100, 500))
+        ops = _fuzz_tape(n, rng, m, style)
+        st = random_state(n, dtype, seed)
+        out, stats = emu_apply(emu, plb, n, ops, st)
+        tol = 5e-12 if dtype == np.complex128 else 3e-4
+        err = float(np.max(np.abs(out - oracle_apply(n, ops, st))))
+        assert err < tol, (seed, n, style, len(ops), err, stats)
