@@ -762,16 +762,18 @@ bool scaled_forms_enabled() {
     return !(e && e[0] == '0');
 }
 
-template <typename T2, class Cfg> void prepare_kernel() {
-    static bool done = false;
-    if (done) return;
+// Opt the kernels into their dynamic shared memory size, once per device (the attribute is per device:
+// DevicePool / batched adjoint runs drive several GPUs from one process).
+template <typename T2, class Cfg> void prepare_kernel(int device) {
+    static bool done[64] = {false};
+    if (device >= 0 && device < 64 && done[device]) return;
     PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem_bytes_for<Cfg, T2>())));
     PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem_bytes_for<Cfg, T2>())));
     PLB_CUDA(cudaFuncSetAttribute(tile_kernel<T2, Cfg, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    done = true;
+    if (device >= 0 && device < 64) done[device] = true;
 }
 template <typename T2, class Cfg>
 void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, double *acc, const PassParams<T2> &pp) {
@@ -786,7 +788,7 @@ void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, double *
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
     using Cfg = FwdCfg<T2>;
     const auto items = as_items(ops);
-    prepare_kernel<T2, Cfg>();
+    prepare_kernel<T2, Cfg>(sv.device);
     // PLB200_FUSE_TRACE=1: per-step device time on stderr (profiling aid; serialises the steps)
     const bool trace = std::getenv("PLB200_FUSE_TRACE") != nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -829,7 +831,7 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
                        double *acc_host, int64_t stats[3]) {
     using Cfg = AdjCfg<T2>;
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
-    prepare_kernel<T2, Cfg>();
+    prepare_kernel<T2, Cfg>(lambda.device);
     // device accumulators: one slab of kMaxPassOps doubles per tile pass; a pass executes >= 2 items
     const size_t max_pass = items.size() / 2 + 1;
     const size_t acc_bytes = max_pass * kMaxPassOps * sizeof(double);
