@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE — not part of the product.  libplb200_emu.so = lowering.cpp + fusion.cu built
+// TEST INFRASTRUCTURE — not part of the product.  tests/_emu/libplb200_emu.so = lowering.cpp + fusion.cu built
 // with -DPLB200_HOST_EMU + this file: the fusion scheduler, the pass encoder and the per-thread tile
 // interpreter (tile_exec.cuh) executed thread-by-thread on HOST memory, so that `-m "not gpu"` tests
 // can check them against the numpy oracle without a GPU.  libplb200.so contains none of this and has

@@ -15,7 +15,7 @@ from pennylane_lightning_b200 import circuits
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "pennylane-lightning_b200", "csrc")
-EMU = os.path.join(os.path.dirname(HERE), "pennylane-lightning_b200", "lib", "libplb200_emu.so")
+EMU = os.path.join(HERE, "_emu", "libplb200_emu.so")
 
 
 @pytest.fixture(scope="module")
