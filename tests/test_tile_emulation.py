@@ -246,3 +246,38 @@ def test_fuzz_random_tapes(emu, plb, multistart, monkeypatch):
         tol = 5e-12 if dtype == np.complex128 else 3e-4
         err = float(np.max(np.abs(out - oracle_apply(n, ops, st))))
         assert err < tol, (seed, n, style, len(ops), err, stats)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.complex128, 12), (np.complex64, 14)])
+def test_edge_case_tapes(emu, plb, dtype, n):
+    """Smallest tiled sizes (n = M + 1) and degenerate tapes: only global phases (a pass that only carries
+    the scalar), only diagonal gates, gates only on the always-resident low bits, stand-alone ops between
+    passes, a 2000-gate single-qubit tape (pass / record caps, repeated scalar flushes), many controls."""
+    rng = np.random.default_rng(0)
+    op = circuits.op
+    tol = 5e-12 if dtype == np.complex128 else 3e-4
+
+    def check(ops, min_passes=1):
+        st = random_state(n, dtype, 3)
+        out, stats = emu_apply(emu, plb, n, ops, st)
+        assert stats[0] >= min_passes, stats
+        assert float(np.max(np.abs(out - oracle_apply(n, ops, st)))) < tol
+
+    check([op("GlobalPhase", [0], [0.3]) for _ in range(5)])
+    check([op("RZ", [int(rng.integers(n))], [rng.uniform(0, 6)]) for _ in range(60)]
+          + [op("CZ", [int(x) for x in rng.permutation(n)[:2]]) for _ in range(40)])
+    check([op("RX", [n - 1 - int(rng.integers(3))], [rng.uniform(0, 6)]) for _ in range(80)])
+    check([op("RX", [0], [0.4])], min_passes=0)
+    check([op("RX", [0], [0.4]), op("IsingXX", [0, 1], [0.2]), op("RY", [1], [0.1]),
+           op("DoubleExcitation", [0, 1, 2, 3], [0.3]), op("RZ", [2], [0.5]), op("RX", [3], [1.0])])
+    long_tape = [op(("RX", "RY", "RZ")[int(rng.integers(3))], [int(rng.integers(n))], [rng.uniform(0, 6)])
+                 for _ in range(2000)]
+    check(long_tape, min_passes=10)
+    many = []
+    for _ in range(40):
+        k = int(rng.integers(3, 7))
+        p = [int(x) for x in rng.permutation(n)[: k + 1]]
+        many.append(op(("RY", "PhaseShift", "RZ")[int(rng.integers(3))], p[:1], [rng.uniform(0, 6)], ctrl_wires=p[1:],
+                       ctrl_values=[bool(b) for b in rng.integers(0, 2, k)]))
+        many.append(op("RX", [int(rng.integers(n))], [rng.uniform(0, 6)]))
+    check(many)
