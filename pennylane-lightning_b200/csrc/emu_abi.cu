@@ -17,6 +17,7 @@ int emulate_fused(int n, int precision, const std::vector<AdjItem> &items, bool 
 
 namespace plb200 {
 void emu_kind_hist(int64_t out[32], bool reset);
+void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]);
 }
 using namespace plb200;
 
@@ -169,6 +170,32 @@ int plb200_emu_schedule(int64_t n, int precision, const plb200_ops_t *ops, int64
         for (int64_t i = 0; i < ops->n_ops; i++)
             for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) all.push_back(std::move(lo));
         schedule_stats(static_cast<int>(n), precision, all, stats4);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// schedule of the backward adjoint sweep only (no states): stats4 as above, -1 in stats4[0] when a
+// trainable generator is not a Pauli word (un-fused route)
+int plb200_emu_adjoint_schedule(int64_t n, int precision, const plb200_ops_t *ops, const int64_t *trainable,
+                                int64_t n_tp, int64_t *stats4) {
+    try {
+        std::vector<GateCall> calls(ops->n_ops);
+        int64_t num_param_ops = 0;
+        for (int64_t i = 0; i < ops->n_ops; i++) {
+            calls[i] = call_from_blob(*ops, i);
+            if (!calls[i].params.empty()) num_param_ops++;
+        }
+        std::vector<AdjItem> items;
+        std::vector<double> sfs;
+        if (!build_adjoint_items(n, calls, std::vector<int64_t>(trainable, trainable + n_tp), num_param_ops, items, sfs)) {
+            stats4[0] = -1;
+            return 0;
+        }
+        emu_adjoint_schedule_stats(static_cast<int>(n), precision, items, stats4);
+        stats4[3] = static_cast<int64_t>(items.size()) * 1000000 + stats4[3] % 1000000; // items packed for reporting
         return 0;
     } catch (const std::exception &e) {
         g_err = e.what();

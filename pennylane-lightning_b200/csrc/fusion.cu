@@ -976,6 +976,16 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
     });
     return rc;
 }
+// schedule-only statistics of the adjoint sweep: {tile passes, stand-alone items, rounds, fused items}
+void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    auto count = [&](const Step &s, const void *) {
+        if (s.op >= 0) out[1]++;
+        else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
+    };
+    if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, count);
+    else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, count);
+}
 void emu_kind_hist(int64_t out[32], bool reset) {
     for (int i = 0; i < 32; i++) {
         out[i] = g_kind_hist[i];
