@@ -135,6 +135,24 @@ int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse);
 /* host-only dry run of the fusion scheduler for an n-qubit state (no device needed):
  * out4 = {tile passes, stand-alone kernels, register rounds, gates executed inside tile passes} */
 int plb200_schedule_stats(int64_t num_qubits, int precision, const plb200_ops_t *ops, int64_t *out4);
+/* Pass specialisation: a fused pass whose structure has been seen before runs as a kernel generated for that
+ * structure and compiled with NVRTC for sm_100a (angles / phases / tile placement stay run-time arguments);
+ * until the kernel exists the generic interpreter kernel runs the pass.  Replaces nothing in the reference
+ * (its gate application is one precompiled kernel per gate, GateImplementationsLM.hpp:650-703).
+ * mode: 0 = off, 1 = compile in the background from the second sighting (default, PLB200_JIT=async),
+ * 2 = compile at first sight, blocking (PLB200_JIT=sync); set_mode(-1) returns to the environment's choice.
+ * stats out8 = {compiled, loaded from the disk cache, launches of compiled kernels, launches left to the
+ * interpreter, failed compiles, compile microseconds, queued + in flight, structures seen}. */
+int plb200_jit_available(void);
+int plb200_jit_mode(void);
+void plb200_jit_set_mode(int mode);
+int plb200_jit_wait(void);
+void plb200_jit_stats(int64_t *out8);
+/* host-only (no device needed): write / compile the specialised source of every tile pass of a tape */
+int plb200_jit_dump_sources(int64_t num_qubits, int precision, const plb200_ops_t *ops, const char *dir,
+                            int64_t *n_passes);
+int plb200_jit_compile_check(int64_t num_qubits, int precision, const plb200_ops_t *ops, int64_t *n_passes,
+                             int64_t *n_ok);
 /* statistics of the last plb200_sv_apply_ops call: [0]=gates, [1]=HBM passes (kernel launches) */
 int plb200_sv_last_apply_stats(const plb200_sv *sv, int64_t *stats2);
 

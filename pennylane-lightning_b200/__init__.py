@@ -16,6 +16,12 @@ from ._capi import (  # noqa: F401
     OpsBlob,
     StateVector,
     build,
+    jit_available,
+    jit_enabled,
+    jit_mode,
+    jit_set_mode,
+    jit_stats,
+    jit_wait,
     lib,
 )
 

@@ -100,6 +100,37 @@ def _c128(a):
     return a, a.ctypes.data_as(_f64p)
 
 
+# ---- pass specialisation (NVRTC) controls, include/plb200.h
+def jit_available() -> bool:
+    return bool(lib().plb200_jit_available())
+
+
+def jit_mode() -> int:
+    """0 = off, 1 = background compilation from the second sighting of a pass structure, 2 = blocking"""
+    return int(lib().plb200_jit_mode())
+
+
+def jit_enabled() -> bool:
+    return jit_mode() != 0 and jit_available()
+
+
+def jit_set_mode(mode: int) -> None:
+    lib().plb200_jit_set_mode(int(mode))
+
+
+def jit_wait() -> None:
+    """Block until every queued pass kernel is compiled (warm-up helper)."""
+    _check(lib().plb200_jit_wait())
+
+
+def jit_stats() -> dict:
+    out = (C.c_int64 * 8)()
+    lib().plb200_jit_stats(out)
+    keys = ("compiled", "from_disk_cache", "jit_launches", "interpreter_launches", "failed", "compile_us", "pending",
+            "structures_seen")
+    return dict(zip(keys, [int(x) for x in out]))
+
+
 class OpsBlob:
     """Flattened tape (plb200_ops_t): the C image of OpsData (JacobianData.hpp:39-253).
 

@@ -17,6 +17,7 @@ int emulate_fused(int n, int precision, const std::vector<AdjItem> &items, bool 
 
 namespace plb200 {
 void emu_kind_hist(int64_t out[32], bool reset);
+int64_t emu_jit_passes();
 void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]);
 }
 using namespace plb200;
@@ -160,6 +161,8 @@ int standalone_cb(void *p, int idx) {
 
 extern "C" {
 const char *plb200_emu_last_error(void) { return g_err.c_str(); }
+// passes executed through the g++-compiled specialised source (PLB200_EMU_JIT=1) so far
+int64_t plb200_emu_jit_passes(void) { return emu_jit_passes(); }
 // ops emitted by the pass encoder per interpreter kind (tile_exec.cuh enum) since the last reset
 void plb200_emu_kind_histogram(int64_t *out32, int reset) { emu_kind_hist(out32, reset != 0); }
 

@@ -15,6 +15,7 @@
 
 #include "device.cuh"
 #include "fusion.hpp"
+#include "jit_runtime.hpp"
 
 using namespace plb200;
 
@@ -580,6 +581,56 @@ int plb200_schedule_stats(int64_t n, int precision, const plb200_ops_t *ops, int
     schedule_stats(static_cast<int>(n), precision, all, out4);
     ABI_CATCH
 }
+// ---- pass specialisation (jit_codegen.hpp / jit_runtime.cpp)
+int plb200_jit_available(void) { return jit::available(nullptr) ? 1 : 0; }
+int plb200_jit_mode(void) { return static_cast<int>(jit::mode()); }
+void plb200_jit_set_mode(int mode) { jit::set_mode(mode); }
+int plb200_jit_wait(void) {
+    ABI_TRY
+    jit::wait_idle();
+    ABI_CATCH
+}
+void plb200_jit_stats(int64_t *out8) { jit::stats(out8); }
+int plb200_jit_dump_sources(int64_t n, int precision, const plb200_ops_t *ops, const char *dir, int64_t *n_passes) {
+    ABI_TRY
+    std::vector<COp> all;
+    for (int64_t i = 0; i < ops->n_ops; i++) {
+        auto l = lower_gate(n, call_from_blob(*ops, i));
+        all.insert(all.end(), std::make_move_iterator(l.begin()), std::make_move_iterator(l.end()));
+    }
+    std::vector<std::string> srcs;
+    pass_sources(static_cast<int>(n), precision, all, srcs);
+    for (size_t i = 0; i < srcs.size(); i++) {
+        const std::string path = std::string(dir) + "/pass_" + std::to_string(i) + ".cu";
+        FILE *f = std::fopen(path.c_str(), "w");
+        PLB_CHECK(f != nullptr, "cannot write " + path);
+        std::fwrite(srcs[i].data(), 1, srcs[i].size(), f);
+        std::fclose(f);
+    }
+    *n_passes = static_cast<int64_t>(srcs.size());
+    ABI_CATCH
+}
+int plb200_jit_compile_check(int64_t n, int precision, const plb200_ops_t *ops, int64_t *n_passes, int64_t *n_ok) {
+    ABI_TRY
+    std::vector<COp> all;
+    for (int64_t i = 0; i < ops->n_ops; i++) {
+        auto l = lower_gate(n, call_from_blob(*ops, i));
+        all.insert(all.end(), std::make_move_iterator(l.begin()), std::make_move_iterator(l.end()));
+    }
+    std::vector<std::string> srcs;
+    pass_sources(static_cast<int>(n), precision, all, srcs);
+    *n_passes = static_cast<int64_t>(srcs.size());
+    *n_ok = 0;
+    for (const auto &src : srcs) {
+        std::string log;
+        size_t bytes = 0;
+        PLB_CHECK(!src.empty(), "a pass has no specialised source");
+        PLB_CHECK(jit::compile_only(src, log, &bytes), "NVRTC: " + log);
+        (*n_ok)++;
+    }
+    ABI_CATCH
+}
+
 int plb200_sv_last_apply_stats(const plb200_sv *sv, int64_t *stats2) {
     stats2[0] = sv->s.last_stats[0];
     stats2[1] = sv->s.last_stats[1];

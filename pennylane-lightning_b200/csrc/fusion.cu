@@ -26,7 +26,17 @@
 #include <cstring>
 #include <memory>
 
+#include "jit_codegen.hpp"
+#include "jit_runtime.hpp"
 #include "tile_exec.cuh"
+
+#if defined(PLB200_HOST_EMU)
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <fstream>
+#include <map>
+#endif
 
 namespace plb200 {
 
@@ -100,6 +110,43 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
 #endif // !PLB200_HOST_EMU
 
 #if defined(PLB200_HOST_EMU)
+// Test-only (PLB200_EMU_JIT=1): the SPECIALISED source of the pass (jit_codegen.hpp) compiled with g++ under
+// -DPLB_JIT_HOST and run thread by thread on host memory, instead of the interpreter.
+int64_t g_emu_jit_passes = 0;
+template <typename T2, class Cfg> bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp) {
+    if constexpr (Cfg::NS != 1) return false;
+    else {
+        const std::string src = jit::generate_pass_source<T2, Cfg>(pp);
+        if (src.empty()) return false;
+        static std::map<uint64_t, void (*)(void *, const void *)> cache;
+        const uint64_t key = jit::fnv1a(src) ^ (static_cast<uint64_t>(src.size()) << 40);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            const char *dir = std::getenv("PLB200_EMU_JIT_DIR");
+            static int serial = 0; // one counter per instantiation: the precision tag keeps the names apart
+            const std::string base = std::string(dir ? dir : "/tmp") + "/plb_jit_" + std::to_string(::getpid()) + "_" +
+                                     (sizeof(T2) == 16 ? "d" : "f") + std::to_string(serial++);
+            {
+                std::ofstream o(base + ".cpp");
+                o << src;
+            }
+            const std::string cmd = "g++ -std=c++17 -O1 -w -shared -fPIC -ffp-contract=off -DPLB_JIT_HOST -o " + base + ".so " + base + ".cpp";
+            if (std::system(cmd.c_str()) != 0) fail("emu jit: g++ failed on " + base + ".cpp");
+            void *h = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (!h) fail(std::string("emu jit: dlopen failed: ") + dlerror());
+            auto fn = reinterpret_cast<void (*)(void *, const void *)>(dlsym(h, "plb_pass_host"));
+            if (!fn) fail("emu jit: plb_pass_host missing");
+            it = cache.emplace(key, fn).first;
+            if (!std::getenv("PLB200_EMU_JIT_KEEP")) {
+                ::unlink((base + ".cpp").c_str());
+                ::unlink((base + ".so").c_str());
+            }
+        }
+        it->second(sv0, &pp);
+        g_emu_jit_passes++;
+        return true;
+    }
+}
 // Thread-by-thread execution of one pass on host memory (test-only emulation, and the reference
 // semantics of tile_kernel: threads of a round are independent, rounds are separated by barriers).
 struct HostReduce {
@@ -791,6 +838,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
     prepare_kernel<T2, Cfg>(sv.device);
     // PLB200_FUSE_TRACE=1: per-step device time on stderr (profiling aid; serialises the steps)
     const bool trace = std::getenv("PLB200_FUSE_TRACE") != nullptr;
+    const bool use_jit = jit::mode() != jit::Mode::Off && sv.n >= jit::min_qubits();
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (trace) {
         PLB_CUDA(cudaEventCreate(&ev0));
@@ -802,7 +850,11 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         if (st.op >= 0) launch_op(sv, ops[st.op]);
         else if (st.op == -2) scale(sv, st.scale);
         else {
-            launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
+            // the pass's specialised kernel when the cache has it (jit_runtime.cpp), else the interpreter
+            jit::Kernel k;
+            if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>());
+            if (k) jit::launch(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream, sv.data, pp);
+            else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
         if (trace) {
@@ -890,6 +942,20 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
     else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, count);
 }
 
+// Host-only: the specialised source of every tile pass of the tape (tools, tests, compile-time checks).
+void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector<std::string> &out) {
+    const auto items = as_items(ops);
+    out.clear();
+    if (precision == 64)
+        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, [&](const Step &s, const PassParams<double2> *pp) {
+            if (s.op == -1) out.push_back(jit::generate_pass_source<double2, FwdCfg<double2>>(*pp));
+        });
+    else
+        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, [&](const Step &s, const PassParams<float2> *pp) {
+            if (s.op == -1) out.push_back(jit::generate_pass_source<float2, FwdCfg<float2>>(*pp));
+        });
+}
+
 bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const std::vector<int64_t> &tp,
                          int64_t num_param_ops, std::vector<AdjItem> &items, std::vector<double> &sfs) {
     const int64_t n_tp = static_cast<int64_t>(tp.size());
@@ -969,7 +1035,8 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
             return;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
+        if (std::getenv("PLB200_EMU_JIT") && emulate_pass_jit<T2, Cfg>(sv0, *pp)) {
+        } else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
         else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
@@ -986,6 +1053,7 @@ void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem>
     if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, count);
     else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, count);
 }
+int64_t emu_jit_passes() { return g_emu_jit_passes; }
 void emu_kind_hist(int64_t out[32], bool reset) {
     for (int i = 0; i < 32; i++) {
         out[i] = g_kind_hist[i];

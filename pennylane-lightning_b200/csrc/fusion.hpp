@@ -1,5 +1,6 @@
 // Tape scheduling: cache-blocked ("tile") execution of a canonical-op list (fusion.cu).
 #pragma once
+#include <string>
 #include <vector>
 
 #include "device.cuh"
@@ -10,6 +11,9 @@ namespace plb200 {
 void run_fused(StateVec &sv, const std::vector<COp> &ops);
 // Host-only: out = {tile passes, stand-alone kernels, rounds, ops executed inside tile passes}
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]);
+
+// Host-only: CUDA source of the specialised kernel of every tile pass of the tape (jit_codegen.hpp)
+void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector<std::string> &out);
 
 // One step of the backward adjoint sweep: either "apply this (already inverted) op to lambda and
 // H lambda" or "accumulate Im<H lambda| P |lambda> into slot" for a (controlled) Pauli word P.

@@ -1,0 +1,507 @@
+// Pass specialisation: CUDA source of ONE fused pass, generated from its encoded description.
+//
+// The tile interpreter (tile_exec.cuh) spends ~40 decode/dispatch instructions per op and thread against
+// 32-48 FP64 instructions of work, plus 12 LOP3/MOV per register pair for every X / CNOT.  A pass kernel
+// generated for the pass's STRUCTURE removes all of that: the op sequence is straight-line code, register
+// permutations (X, CNOT and SWAP on register bits) are renamings done here at generation time (zero
+// instructions), controls / parities on thread bits are compare-with-immediate, shared-memory offsets are
+// immediates, and diagonal factors that do not depend on a register bit are multiplied into ONE scalar per
+// thread and round.  Everything numeric (angles, phases, the positions of the tile bits, masks over bits
+// outside the tile) stays a RUN-TIME argument read from the same PassParams block the interpreter takes
+// (constant bank operands), so one compiled kernel serves every parameter set of a variational circuit
+// and every tile placement.  The structure key is the generated text.
+//
+// The text compiles (a) with NVRTC for sm_100a (jit_runtime.cpp) and (b) with g++ under -DPLB_JIT_HOST,
+// which tests use to run the generated per-thread code on host memory against the oracle.
+#pragma once
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "tile_exec.cuh"
+
+namespace plb200 {
+namespace jit {
+
+using namespace tile;
+
+inline const char *prelude() {
+    return R"PLB(
+#if defined(PLB_JIT_HOST)
+#include <cmath>
+#include <cstdint>
+#include <cstddef>
+typedef uint32_t u32;
+typedef uint64_t u64;
+#define DEV static inline
+#define POPC(x) __builtin_popcount(x)
+#define POPCLL(x) __builtin_popcountll(x)
+#define PLB_ALIGN(n) alignas(n)
+using std::fma;
+#if PLB_DOUBLE
+typedef double real;
+struct alignas(16) T2 { real x, y; };
+#else
+typedef float real;
+struct alignas(8) T2 { real x, y; };
+#endif
+#else
+typedef unsigned int u32;
+typedef unsigned long long u64;
+#define DEV __device__ __forceinline__
+#define POPC(x) __popc(x)
+#define POPCLL(x) __popcll(x)
+#define PLB_ALIGN(n) __align__(n)
+#if PLB_DOUBLE
+typedef double real;
+typedef double2 T2;
+#else
+typedef float real;
+typedef float2 T2;
+#endif
+#endif
+
+struct BitInsert { int n; u64 lowmask[40]; };
+struct PLB_ALIGN(16) TileOp {
+    u32 code, cm_tid, cv_tid, pm_tid, umask, upar, slot;
+    u64 cmask_o, cval_o, pmask_o;
+    T2 m[4];
+};
+struct PLB_ALIGN(16) LadderEntry { u64 cmask_o; u32 cm_tid, pad; T2 ph; };
+struct PLB_ALIGN(16) RoundHdr { int first_op, nops, nlad, pad; u32 w[9]; u32 sroff[32]; };
+struct PLB_ALIGN(16) PassHdr { int nrounds, nops_total; u64 ntiles; int nslots, pad; BitInsert tile_ins; };
+struct PLB_ALIGN(16) PassParams { PassHdr hdr; RoundHdr rounds[PLB_MAXROUNDS]; TileOp ops[PLB_MAXOPS + 1]; };
+static_assert(sizeof(TileOp) == PLB_SIZEOF_TILEOP, "TileOp layout");
+static_assert(sizeof(PassParams) == PLB_SIZEOF_PASSPARAMS, "PassParams layout");
+static_assert(sizeof(PassHdr) + PLB_MAXROUNDS * sizeof(RoundHdr) == PLB_OFFSETOF_OPS, "PassParams layout");
+
+DEV void cmul_ip(T2 &v, const T2 d) {
+    const real t = v.x * d.y;
+    v.x = v.x * d.x;
+    v.x = fma(-v.y, d.y, v.x);
+    v.y = fma(v.y, d.x, t);
+}
+DEV void cshear_ip(T2 &a, const T2 t, const T2 &b) {
+    a.x = fma(t.x, b.x, a.x);
+    a.x = fma(-t.y, b.y, a.x);
+    a.y = fma(t.x, b.y, a.y);
+    a.y = fma(t.y, b.x, a.y);
+}
+DEV void cswap(T2 &a, T2 &b) { const T2 t = a; a = b; b = t; }
+DEV void lift_r(T2 &a, T2 &b, const T2 m) {
+    a.x = fma(m.x, b.x, a.x), a.y = fma(m.x, b.y, a.y);
+    b.x = fma(m.y, a.x, b.x), b.y = fma(m.y, a.y, b.y);
+    a.x = fma(m.x, b.x, a.x), a.y = fma(m.x, b.y, a.y);
+}
+DEV void lift_i(T2 &a, T2 &b, const T2 m) {
+    a.x = fma(-m.x, b.y, a.x), a.y = fma(m.x, b.x, a.y);
+    b.x = fma(-m.y, a.y, b.x), b.y = fma(m.y, a.x, b.y);
+    a.x = fma(-m.x, b.y, a.x), a.y = fma(m.x, b.x, a.y);
+}
+DEV void had(T2 &a, T2 &b) {
+    a.x = a.x + b.x, a.y = a.y + b.y;
+    b.x = fma((real)-2, b.x, a.x), b.y = fma((real)-2, b.y, a.y);
+}
+DEV void lu_r(T2 &a, T2 &b, const T2 m0, const T2 m1) {
+    a.x = fma(m0.x, b.x, a.x), a.y = fma(m0.x, b.y, a.y);
+    b.x = fma(m0.y, a.x, b.x), b.y = fma(m0.y, a.y, b.y);
+    a.x = a.x * m1.x, a.y = a.y * m1.x;
+    b.x = b.x * m1.y, b.y = b.y * m1.y;
+}
+DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) {
+    cshear_ip(a, m0, b);
+    cshear_ip(b, m1, a);
+    cmul_ip(a, m2);
+    cmul_ip(b, m3);
+}
+DEV u64 insert_bits_m(u64 x, const BitInsert &bi) {
+#pragma unroll
+    for (int i = 0; i < PLB_M; i++) {
+        const u64 lm = bi.lowmask[i];
+        x = ((x & ~lm) << 1) | (x & lm);
+    }
+    return x;
+}
+DEV u64 tile_line_offset(const PassHdr &h, int i) {
+    u64 o = 0;
+#pragma unroll
+    for (int b = PLB_LOW; b < PLB_M; b++)
+        if ((i >> (b - PLB_LOW)) & 1) o |= h.tile_ins.lowmask[b] + 1;
+    return o;
+}
+// shared-memory swizzle of tile_exec.cuh (Swz<T2>): element j lives at j ^ g(j)
+DEV constexpr u32 swz(u32 j) {
+    u32 g = 0;
+    for (int i = PLB_SWZ_B; i < 13; i++)
+        if ((j >> i) & 1u) g ^= (u32)((PLB_SWZ_COLS >> (4 * i)) & 15ull);
+    return j ^ g;
+}
+#define PLB_NV (1 << PLB_R)
+DEV void load_tile(u32 tid, u64 base, const u64 *goff, const T2 *__restrict__ sv, unsigned char *smem) {
+    const u32 st = swz(tid) * (u32)sizeof(T2);
+    T2 v[PLB_NV];
+#pragma unroll
+    for (int u = 0; u < PLB_NV; u++) {
+        const u32 j = tid + u * PLB_NT;
+        v[u] = sv[base | goff[j >> PLB_LOW] | (j & ((1u << PLB_LOW) - 1))];
+    }
+#pragma unroll
+    for (int u = 0; u < PLB_NV; u++) *(T2 *)(smem + (st ^ (swz(u * PLB_NT) * (u32)sizeof(T2)))) = v[u];
+}
+DEV void store_tile(u32 tid, u64 base, const u64 *goff, T2 *__restrict__ sv, const unsigned char *smem) {
+    const u32 st = swz(tid) * (u32)sizeof(T2);
+    T2 v[PLB_NV];
+#pragma unroll
+    for (int u = 0; u < PLB_NV; u++) v[u] = *(const T2 *)(smem + (st ^ (swz(u * PLB_NT) * (u32)sizeof(T2))));
+#pragma unroll
+    for (int u = 0; u < PLB_NV; u++) {
+        const u32 j = tid + u * PLB_NT;
+        sv[base | goff[j >> PLB_LOW] | (j & ((1u << PLB_LOW) - 1))] = v[u];
+    }
+}
+)PLB";
+}
+
+inline const char *kernel_text() {
+    return R"PLB(
+#if defined(PLB_JIT_HOST)
+// test-only: the generated per-thread code run thread by thread on host memory (rounds are separated
+// by barriers on the device, so each phase is completed for every thread before the next starts)
+extern "C" void plb_pass_host(T2 *sv, const PassParams *ppp) {
+    const PassParams &pp = *ppp;
+    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)];
+    static u64 goff[1 << (PLB_M - PLB_LOW)];
+    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);
+    for (u64 t = 0; t < pp.hdr.ntiles; t++) {
+        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);
+        for (u32 tid = 0; tid < PLB_NT; tid++) load_tile(tid, base, goff, sv, smem);
+        PLB_HOST_ROUNDS
+        for (u32 tid = 0; tid < PLB_NT; tid++) store_tile(tid, base, goff, sv, smem);
+    }
+}
+#else
+extern "C" __global__ void __launch_bounds__(PLB_NT, PLB_MINB)
+    plb_pass(T2 *__restrict__ sv, const __grid_constant__ PassParams pp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64 *goff = (u64 *)(smem + (sizeof(T2) << PLB_M));
+    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);
+    __syncthreads();
+    const u32 tid = threadIdx.x;
+    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
+        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);
+        if (t + gridDim.x < pp.hdr.ntiles) {
+            const u64 nbase = insert_bits_m(t + gridDim.x, pp.hdr.tile_ins);
+            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv + (nbase | goff[l])));
+        }
+        load_tile(tid, base, goff, sv, smem);
+        __syncthreads();
+        PLB_DEVICE_ROUNDS
+        store_tile(tid, base, goff, sv, smem);
+        __syncthreads();
+    }
+}
+#endif
+)PLB";
+}
+
+template <typename T2, class Cfg> class Gen {
+    static constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NV = 1 << R, NTB = M - R;
+    const PassParams<T2> &pp;
+    std::string s;
+    int perm[NV]; // logical register u lives in variable v<perm[u]>
+
+    void add(const char *fmt, ...) __attribute__((format(printf, 2, 3))) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        s += buf;
+    }
+    static std::string hex(uint32_t v) {
+        char b[16];
+        snprintf(b, sizeof(b), "0x%xu", v);
+        return b;
+    }
+    std::string V(int u) const { return "v" + std::to_string(perm[u]); }
+
+    // condition of op K: tile-uniform part (outside controls) and thread part
+    std::string cond_of(const TileOp<T2> &op, int K) const {
+        std::string c;
+        if (op.cmask_o) c += "((base & pp.ops[" + std::to_string(K) + "].cmask_o) == pp.ops[" + std::to_string(K) + "].cval_o)";
+        if (op.cm_tid) {
+            if (!c.empty()) c += " && ";
+            c += "((tid & " + hex(op.cm_tid) + ") == " + hex(op.cv_tid) + ")";
+        }
+        return c;
+    }
+    // parity expression of op K, or "" when it has none
+    std::string par_of(const TileOp<T2> &op, int K) const {
+        std::string p;
+        if (op.pm_tid) p += "POPC(tid & " + hex(op.pm_tid) + ")";
+        if (op.pmask_o) {
+            if (!p.empty()) p += " + ";
+            p += "POPCLL(base & pp.ops[" + std::to_string(K) + "].pmask_o)";
+        }
+        if (p.empty()) return p;
+        return "(((" + p + ") & 1) != 0)";
+    }
+
+    void gen_round(int r) {
+        const RoundHdr &rh = pp.rounds[r];
+        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem) {\n", r);
+        // thread part of the swizzled offset
+        s += "    const u32 sb = 0u";
+        for (int i = 0; i < NTB; i++) add(" ^ ((tid >> %d & 1u) * %s)", i, hex(rh.w[i]).c_str());
+        s += ";\n";
+        // register loads: the swizzle only mixes into the bank-group bits, everything above is a plain offset
+        const uint32_t lowmask = ((1u << Swz<T2>::B) - 1u) * static_cast<uint32_t>(sizeof(T2));
+        std::vector<uint32_t> lows;
+        auto low_id = [&](uint32_t low) {
+            for (size_t i = 0; i < lows.size(); i++)
+                if (lows[i] == low) return static_cast<int>(i);
+            lows.push_back(low);
+            return static_cast<int>(lows.size() - 1);
+        };
+        for (int u = 0; u < NV; u++) low_id(rh.sroff[u] & lowmask);
+        for (size_t i = 0; i < lows.size(); i++)
+            add("    unsigned char *const b%zu = smem + (sb ^ %s);\n", i, hex(lows[i]).c_str());
+        for (int u = 0; u < NV; u++) {
+            perm[u] = u;
+            add("    T2 v%d = *(const T2 *)(b%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
+        }
+        // thread-scalar diagonal factors of this round (K_DIAG_T / K_DIAG1_T): merged when there are >= 2
+        int n_tscalar = 0;
+        for (int k = 0; k < rh.nops; k++) {
+            const int kind = code_kind(pp.ops[rh.first_op + k].code);
+            if (kind == K_DIAG_T || kind == K_DIAG1_T) n_tscalar++;
+        }
+        const bool merge_ts = n_tscalar >= 2;
+        if (merge_ts) s += "    T2 ts; ts.x = (real)1; ts.y = (real)0; bool ts_any = false;\n";
+
+        for (int k = 0; k < rh.nops; k++) gen_op(rh.first_op + k, merge_ts);
+
+        if (merge_ts) {
+            s += "    if (ts_any) {\n";
+            for (int u = 0; u < NV; u++) add("        cmul_ip(%s, ts);\n", V(u).c_str());
+            s += "    }\n";
+        }
+        gen_ladders(rh);
+        for (int u = 0; u < NV; u++)
+            add("    *(T2 *)(b%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), V(u).c_str());
+        s += "}\n";
+    }
+
+    // pairs (u0, u1) on register bit P
+    static void pairs_on(int P, std::vector<std::pair<int, int>> &out) {
+        out.clear();
+        for (int q = 0; q < (1 << (R - 1)); q++) {
+            const int u0 = ((q >> P) << (P + 1)) | (q & ((1 << P) - 1));
+            out.emplace_back(u0, u0 | (1 << P));
+        }
+    }
+
+    void gen_op(int K, bool merge_ts) {
+        const TileOp<T2> &op = pp.ops[K];
+        const uint32_t code = op.code;
+        const int kind = code_kind(code), P = code_p(code), C = static_cast<int>((code >> 16) & 7u);
+        const std::string cond = (code & F_COND) ? cond_of(op, K) : std::string();
+        const std::string par = (code & F_PAR) ? par_of(op, K) : std::string();
+        const std::string O = "pp.ops[" + std::to_string(K) + "]";
+        std::vector<std::pair<int, int>> pr;
+        add("    { // op %d kind %d P %d C %d\n", K, kind, P, C);
+        auto open_cond = [&]() {
+            if (!cond.empty()) s += "        if (" + cond + ") {\n";
+        };
+        auto close_cond = [&]() {
+            if (!cond.empty()) s += "        }\n";
+        };
+        auto decl_m = [&](int n) {
+            for (int q = 0; q < n; q++) add("        const T2 m%d = %s.m[%d];\n", q, O.c_str(), q);
+        };
+        // phases of a two-valued diagonal: dA (parity 0) / dB (parity 1) after the thread / outside parity
+        auto decl_dab = [&]() {
+            decl_m(2);
+            if (par.empty()) s += "        const T2 dA = m0, dB = m1;\n";
+            else {
+                s += "        const bool pt = " + par + ";\n";
+                s += "        const T2 dA = pt ? m1 : m0, dB = pt ? m0 : m1;\n";
+            }
+        };
+        switch (kind) {
+        case K_LIFT_R: case K_LIFT_I: case K_HAD: case K_LU_R: case K_LU_C:
+        case K_LIFT_R_M: case K_LIFT_I_M: case K_LU_R_M: case K_LU_C_M: {
+            const bool masked = kind >= K_LIFT_R_M;
+            const int base_kind = kind == K_LIFT_R_M ? K_LIFT_R : kind == K_LIFT_I_M ? K_LIFT_I
+                                  : kind == K_LU_R_M ? K_LU_R : kind == K_LU_C_M ? K_LU_C : kind;
+            decl_m(base_kind == K_LU_C ? 4 : base_kind == K_LU_R ? 2 : base_kind == K_HAD ? 0 : 1);
+            open_cond();
+            pairs_on(P, pr);
+            for (auto [u0, u1] : pr) {
+                if (masked && !((op.umask >> u0) & 1u)) continue;
+                const std::string a = V(u0), b = V(u1);
+                switch (base_kind) {
+                case K_LIFT_R: add("            lift_r(%s, %s, m0);\n", a.c_str(), b.c_str()); break;
+                case K_LIFT_I: add("            lift_i(%s, %s, m0);\n", a.c_str(), b.c_str()); break;
+                case K_HAD: add("            had(%s, %s);\n", a.c_str(), b.c_str()); break;
+                case K_LU_R: add("            lu_r(%s, %s, m0, m1);\n", a.c_str(), b.c_str()); break;
+                default: add("            lu_c(%s, %s, m0, m1, m2, m3);\n", a.c_str(), b.c_str()); break;
+                }
+            }
+            close_cond();
+        } break;
+        case K_SWAP: case K_SWAP_M: case K_SWAP_CR: case K_SWAP2: case K_SWAP2_M: {
+            pr.clear();
+            if (kind == K_SWAP2 || kind == K_SWAP2_M) {
+                for (int u = 0; u < NV; u++) {
+                    if (((u >> P) & 1) || ((u >> C) & 1)) continue;
+                    const int ua = u | (1 << P), ub = u | (1 << C);
+                    if (kind == K_SWAP2_M && !((op.umask >> ua) & 1u)) continue;
+                    pr.emplace_back(ua, ub);
+                }
+            } else {
+                std::vector<std::pair<int, int>> all;
+                pairs_on(P, all);
+                for (auto [u0, u1] : all) {
+                    if (kind == K_SWAP_M && !((op.umask >> u0) & 1u)) continue;
+                    if (kind == K_SWAP_CR && !((u0 >> C) & 1)) continue;
+                    pr.emplace_back(u0, u1);
+                }
+            }
+            if (cond.empty()) { // a renaming: no instructions
+                for (auto [a, b] : pr) std::swap(perm[a], perm[b]);
+                s += "        // register renaming\n";
+            } else {
+                open_cond();
+                for (auto [a, b] : pr) add("            cswap(%s, %s);\n", V(a).c_str(), V(b).c_str());
+                close_cond();
+            }
+        } break;
+        case K_DIAG_R: case K_DIAG_PP: case K_DIAG_CR: {
+            decl_dab();
+            open_cond();
+            for (int u = 0; u < NV; u++) {
+                if (kind == K_DIAG_CR && !((u >> C) & 1)) continue;
+                const bool odd = kind == K_DIAG_PP ? ((((u >> P) ^ (u >> C)) & 1) != 0) : (((u >> P) & 1) != 0);
+                add("            cmul_ip(%s, %s);\n", V(u).c_str(), odd ? "dB" : "dA");
+            }
+            close_cond();
+        } break;
+        case K_DIAG1_R: {
+            decl_m(1);
+            open_cond();
+            for (int u = 0; u < NV; u++)
+                if ((u >> P) & 1) add("            cmul_ip(%s, m0);\n", V(u).c_str());
+            close_cond();
+        } break;
+        case K_DIAG_T: case K_DIAG1_T: case K_DIAG_CT: {
+            // one scalar for all registers (K_DIAG_CT: for the registers whose bit P is set)
+            if (kind == K_DIAG1_T) {
+                decl_m(1);
+                if (par.empty()) break; // parity 0 everywhere: identity
+                s += "        const bool pt = " + par + ";\n        const T2 d = m0;\n";
+            } else {
+                decl_m(2);
+                if (par.empty()) s += "        const T2 d = m0;\n";
+                else s += "        const bool pt = " + par + ";\n        const T2 d = pt ? m1 : m0;\n";
+            }
+            std::string c2 = cond;
+            if (kind == K_DIAG1_T) c2 = c2.empty() ? "pt" : "(" + c2 + ") && pt";
+            if (!c2.empty()) s += "        if (" + c2 + ") {\n";
+            if (kind != K_DIAG_CT && merge_ts) s += "            cmul_ip(ts, d); ts_any = true;\n";
+            else
+                for (int u = 0; u < NV; u++) {
+                    if (kind == K_DIAG_CT && !((u >> P) & 1)) continue;
+                    add("            cmul_ip(%s, d);\n", V(u).c_str());
+                }
+            if (!c2.empty()) s += "        }\n";
+        } break;
+        case K_DIAG_G: {
+            decl_dab(); // dA: parity bit 0 after the thread parity, dB: 1
+            open_cond();
+            for (int u = 0; u < NV; u++) {
+                if (!((op.umask >> u) & 1u)) continue;
+                add("            cmul_ip(%s, %s);\n", V(u).c_str(), ((op.upar >> u) & 1u) ? "dB" : "dA");
+            }
+            close_cond();
+        } break;
+        default: ok = false; break;
+        }
+        s += "    }\n";
+    }
+
+    void gen_ladders(const RoundHdr &rh) {
+        const int first = rh.first_op + rh.nops;
+        constexpr int per = ladder_entries_per_record<T2>();
+        for (int q = 0; q < rh.nlad;) {
+            const TileOp<T2> &hd = pp.ops[first + q];
+            const int n = static_cast<int>(hd.slot), p = code_p(hd.code);
+            const LadderEntry<T2> *en = reinterpret_cast<const LadderEntry<T2> *>(&pp.ops[first + q + 1]);
+            add("    { // ladder of %d controlled phases on register bit %d\n", n, p);
+            add("        const LadderEntry *en = (const LadderEntry *)&pp.ops[%d];\n", first + q + 1);
+            s += "        T2 t; t.x = (real)1; t.y = (real)0; bool any = false;\n";
+            for (int e = 0; e < n; e++) {
+                std::string c;
+                if (en[e].cmask_o) c = "((base & en[" + std::to_string(e) + "].cmask_o) == en[" + std::to_string(e) + "].cmask_o)";
+                if (en[e].cm_tid) {
+                    if (!c.empty()) c += " && ";
+                    c += "((tid & " + hex(en[e].cm_tid) + ") == " + hex(en[e].cm_tid) + ")";
+                }
+                if (c.empty()) add("        cmul_ip(t, en[%d].ph); any = true;\n", e);
+                else add("        if (%s) { cmul_ip(t, en[%d].ph); any = true; }\n", c.c_str(), e);
+            }
+            s += "        if (any) {\n";
+            for (int u = 0; u < NV; u++)
+                if (p >= R || ((u >> p) & 1)) add("            cmul_ip(%s, t);\n", V(u).c_str());
+            s += "        }\n    }\n";
+            q += 1 + (n + per - 1) / per;
+        }
+    }
+
+    // resident CTAs per SM the kernel is compiled for (register cap); PLB200_JIT_MINB overrides (tuning)
+    static int minb() {
+        const char *e = std::getenv("PLB200_JIT_MINB");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : Cfg::MINB;
+    }
+
+  public:
+    bool ok = true;
+    explicit Gen(const PassParams<T2> &p) : pp(p) {}
+
+    std::string run() {
+        constexpr bool dbl = sizeof(T2) == 16;
+        add("#define PLB_DOUBLE %d\n#define PLB_M %d\n#define PLB_LOW %d\n#define PLB_R %d\n#define PLB_NT %d\n#define PLB_MINB %d\n",
+            dbl ? 1 : 0, M, LOW, R, 1 << NTB, minb());
+        add("#define PLB_MAXROUNDS %d\n#define PLB_MAXOPS %d\n#define PLB_SWZ_B %d\n#define PLB_SWZ_COLS 0x%llxull\n", kMaxPassRounds,
+            kMaxPassOps, Swz<T2>::B, static_cast<unsigned long long>(Swz<T2>::cols));
+        add("#define PLB_SIZEOF_TILEOP %zu\n#define PLB_SIZEOF_PASSPARAMS %zu\n#define PLB_OFFSETOF_OPS %zu\n", sizeof(TileOp<T2>),
+            sizeof(PassParams<T2>), offsetof(PassParams<T2>, ops));
+        s += prelude();
+        for (int r = 0; r < pp.hdr.nrounds; r++) gen_round(r);
+        std::string dev, host;
+        for (int r = 0; r < pp.hdr.nrounds; r++) {
+            dev += "round_" + std::to_string(r) + "(pp, tid, base, smem); __syncthreads(); ";
+            host += "for (u32 tid = 0; tid < PLB_NT; tid++) round_" + std::to_string(r) + "(pp, tid, base, smem); ";
+        }
+        s += "#define PLB_DEVICE_ROUNDS " + dev + "\n#define PLB_HOST_ROUNDS " + host + "\n";
+        s += kernel_text();
+        return s;
+    }
+};
+
+// Source of the specialised kernel of a forward pass, or "" when the pass holds an op kind the generator
+// does not cover (the interpreter kernel then runs it).
+template <typename T2, class Cfg> std::string generate_pass_source(const PassParams<T2> &pp) {
+    static_assert(Cfg::NS == 1, "forward passes only");
+    Gen<T2, Cfg> g(pp);
+    std::string src = g.run();
+    return g.ok ? src : std::string();
+}
+
+} // namespace jit
+} // namespace plb200

@@ -90,8 +90,11 @@ template <class Precision = double> class StateVectorB200 {
         PLB200_ABI(plb200_sv_d2d(h_, other.handle()));
     }
     StateVectorB200 &operator=(const StateVectorB200 &) = delete;
-    StateVectorB200(StateVectorB200 &&o) noexcept : h_{o.h_}, num_qubits_{o.num_qubits_}, dev_tag_{o.dev_tag_} {
+    // the lazily queued gates travel with the handle (a moved-from object owns nothing)
+    StateVectorB200(StateVectorB200 &&o) noexcept
+        : h_{o.h_}, num_qubits_{o.num_qubits_}, dev_tag_{o.dev_tag_}, lazy_{o.lazy_}, queue_{std::move(o.queue_)} {
         o.h_ = nullptr;
+        o.queue_ = detail::OpsBlob{};
     }
     ~StateVectorB200() {
         if (h_) plb200_sv_destroy(h_);

@@ -124,6 +124,71 @@ def worker(rank, world, n, seed, port, backend, q, swap="auto"):
         dist.destroy_process_group()
 
 
+def multicall_tapes(n, seed):
+    """Several apply_ops calls whose controlled gates sit on (possibly) global wires with no later use of
+    the target: the case where a rank-dependent control skip used to make the ranks' schedules diverge."""
+    from pennylane_lightning_b200 import circuits
+
+    rng = np.random.default_rng(seed)
+    tapes = [[circuits.op("RY", [w], [0.3 + 0.1 * w]) for w in range(n)]]
+    for _ in range(4):
+        t = []
+        for _ in range(n):
+            p = [int(x) for x in rng.permutation(n)]
+            r = rng.random()
+            if r < 0.4:
+                t.append(circuits.op("CNOT", p[:2]))
+            elif r < 0.6:
+                t.append(circuits.op("RX", p[:1], [rng.uniform(0, 6)]))
+            elif r < 0.75:
+                t.append(circuits.op("CRY", p[:2], [rng.uniform(0, 6)]))
+            elif r < 0.9:
+                t.append(circuits.op("Toffoli", p[:3]))
+            else:
+                t.append(circuits.op("RX", p[:1], [rng.uniform(0, 6)], ctrl_wires=p[1:3], ctrl_values=[False, True]))
+        tapes.append(t)
+    # the advisor's reproducer (n >= 6): controlled gate with control and target both global, then more ops
+    tapes.append([circuits.op("CNOT", [2 % n, 3 % n]), circuits.op("RX", [2 % n], [0.7]),
+                  circuits.op("CNOT", [4 % n, 5 % n]), circuits.op("RX", [3 % n], [0.9]),
+                  circuits.op("CNOT", [0, 4 % n]), circuits.op("RX", [1], [1.1])])
+    return tapes
+
+
+def worker_multicall(rank, world, n, seed, port, backend, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    from pennylane_lightning_b200.dist import DistStateVector
+
+    try:
+        sv = DistStateVector(n, np.complex128, engine_factory=NumpyEngine)
+        for t in multicall_tapes(n, seed):
+            sv.apply_ops(t, fuse=True)
+        phys = [None] * world
+        dist.all_gather_object(phys, list(sv.phys))
+        full = sv.gather_state()
+        if rank == 0:
+            q.put(dict(state=full, phys=phys, swaps=sv.n_swaps))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_ranks_multicall(world, n, seed, port):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker_multicall, args=(r, world, n, seed, port, "gloo", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    return res
+
+
 def run_ranks(world, n, seed, backend="gloo", port=29611, swap="auto"):
     import torch.multiprocessing as mp
 

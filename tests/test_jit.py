@@ -1,0 +1,172 @@
+"""Pass specialisation (csrc/jit_codegen.hpp + jit_runtime.cpp): the NVRTC-compiled kernel of a fused pass must
+give the interpreter kernel's and the reference's amplitudes.
+
+CPU (`-m "not gpu"`): every pass of a tape has a specialised source, NVRTC compiles it for sm_100a (no device
+needed), and the SAME generated text, compiled with g++ under -DPLB_JIT_HOST by the test-only emulation
+library, run thread by thread on host memory, matches the numpy oracle.
+GPU (`-m gpu`): compiled kernels vs interpreter vs lightning.qubit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import TOL, random_state
+from pennylane_lightning_b200 import circuits
+
+
+def _mixed_tape(n, seed, count=160):
+    rng = np.random.default_rng(seed)
+    names1 = ["Hadamard", "PauliX", "PauliY", "PauliZ", "S", "SX", "T", "RX", "RY", "RZ", "PhaseShift", "Rot"]
+    names2 = ["CNOT", "CZ", "CY", "SWAP", "CRX", "CRY", "CRZ", "CRot", "ControlledPhaseShift", "IsingZZ"]
+    npar = {"RX": 1, "RY": 1, "RZ": 1, "PhaseShift": 1, "Rot": 3, "CRX": 1, "CRY": 1, "CRZ": 1, "CRot": 3,
+            "ControlledPhaseShift": 1, "IsingZZ": 1}
+    ops = []
+    for _ in range(count):
+        r = rng.random()
+        if r < 0.45:
+            nm = names1[int(rng.integers(len(names1)))]
+            ops.append(circuits.op(nm, [int(rng.integers(n))], rng.uniform(0, 6, npar.get(nm, 0)),
+                                   inverse=bool(rng.integers(2))))
+        elif r < 0.8:
+            nm = names2[int(rng.integers(len(names2)))]
+            ops.append(circuits.op(nm, [int(x) for x in rng.permutation(n)[:2]], rng.uniform(0, 6, npar.get(nm, 0)),
+                                   inverse=bool(rng.integers(2))))
+        elif r < 0.9:
+            p = [int(x) for x in rng.permutation(n)]
+            ops.append(circuits.op(("RX", "RY", "RZ", "PauliX", "PhaseShift")[int(rng.integers(5))], p[:1],
+                                   rng.uniform(0, 6, 1) if rng.random() < 2 else (), ctrl_wires=p[1:3],
+                                   ctrl_values=[bool(rng.integers(2)), bool(rng.integers(2))]))
+            if ops[-1]["name"] == "PauliX":
+                ops[-1]["params"] = []
+        else:
+            p = [int(x) for x in rng.permutation(n)]
+            ops.append(circuits.op("MultiRZ", p[:3], [rng.uniform(0, 6)]))
+    return ops
+
+
+# ------------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("prec", [64, 32])
+@pytest.mark.parametrize("kind", ["random", "qft"])
+def test_every_pass_compiles_with_nvrtc(plb, prec, kind):
+    if not plb.jit_available() and not os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12"):
+        pytest.skip("NVRTC not present")
+    n = 20
+    ops = circuits.random_circuit(n, 3, 1234) if kind == "random" else circuits.qft(n)
+    blob = plb.OpsBlob(ops)
+    npass, nok = C.c_int64(), C.c_int64()
+    rc = plb.lib().plb200_jit_compile_check(C.c_int64(n), prec, blob.ptr(), C.byref(npass), C.byref(nok))
+    assert rc == 0, plb.lib().plb200_last_error()
+    assert npass.value >= 1 and nok.value == npass.value
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_generated_code_on_host_matches_oracle(plb, dtype, monkeypatch):
+    from test_tile_emulation import emu_apply, oracle_apply, emu as _emu_fixture  # noqa: F401
+
+    emu = _emu_fixture.__wrapped__() if hasattr(_emu_fixture, "__wrapped__") else None
+    if emu is None:
+        import subprocess
+
+        from test_tile_emulation import CSRC, EMU
+
+        res = subprocess.run(["make", "-C", CSRC, "-j8", "emu"], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        emu = C.CDLL(EMU)
+        emu.plb200_emu_last_error.restype = C.c_char_p
+    emu.plb200_emu_jit_passes.restype = C.c_int64
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 15 if dtype == np.complex128 else 16
+    before = emu.plb200_emu_jit_passes()
+    for ops in (circuits.random_circuit(n, 3, 99), _mixed_tape(n, 5, 90), circuits.qft(n)):
+        st = random_state(n, dtype, 2)
+        out, stats = emu_apply(emu, plb, n, ops, st, True)
+        np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=TOL[np.dtype(dtype)])
+    assert emu.plb200_emu_jit_passes() > before
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.fixture
+def jit_sync(plb, monkeypatch):
+    if not plb.jit_available():
+        pytest.fail("NVRTC / libcuda could not be loaded on a GPU box")
+    monkeypatch.setenv("PLB200_JIT_MIN_QUBITS", "12")
+    plb.jit_set_mode(2)
+    yield
+    plb.jit_set_mode(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("kind", ["random", "mixed", "qft", "sel"])
+def test_jit_kernels_match_interpreter_and_reference(plb, ref, jit_sync, dtype, kind):
+    n = 18
+    ops = {"random": lambda: circuits.random_circuit(n, 6, 1234), "mixed": lambda: _mixed_tape(n, 7, 300),
+           "qft": lambda: circuits.qft(n), "sel": lambda: circuits.strongly_entangling_layers(n, 3, 42)[0]}[kind]()
+    st = random_state(n, dtype, 3)
+    before = plb.jit_stats()
+    a = plb.StateVector(n, dtype)
+    a.set_state(st)
+    a.apply_ops(ops, fuse=True)
+    got = a.get_state()
+    after = plb.jit_stats()
+    assert after["jit_launches"] > before["jit_launches"], (before, after)
+    assert after["failed"] == before["failed"]
+    plb.jit_set_mode(0)
+    b = plb.StateVector(n, dtype)
+    b.set_state(st)
+    b.apply_ops(ops, fuse=True)
+    interp = b.get_state()
+    plb.jit_set_mode(2)
+    r = ref.StateVector(n, dtype)
+    r.set_state(st)
+    r.apply_ops(ops)
+    tol = TOL[np.dtype(dtype)]
+    np.testing.assert_allclose(got, r.get_state(), rtol=0, atol=tol)
+    np.testing.assert_allclose(got, interp, rtol=0, atol=tol)
+
+
+@pytest.mark.gpu
+def test_jit_async_tiering(plb, monkeypatch):
+    """Default mode: first sighting runs the interpreter, the second queues a background compile, after
+    jit_wait() the compiled kernel runs — and all three give the same state."""
+    if not plb.jit_available():
+        pytest.fail("NVRTC / libcuda could not be loaded on a GPU box")
+    monkeypatch.setenv("PLB200_JIT_MIN_QUBITS", "12")
+    plb.jit_set_mode(1)
+    try:
+        n = 17
+        ops = circuits.random_circuit(n, 5, 4321)
+        states = []
+        s0 = plb.jit_stats()
+        for it in range(3):
+            sv = plb.StateVector(n)
+            sv.apply_ops(ops, fuse=True)
+            states.append(sv.get_state())
+            if it == 1:
+                plb.jit_wait()
+        s1 = plb.jit_stats()
+        assert s1["compiled"] + s1["from_disk_cache"] > s0["compiled"] + s0["from_disk_cache"]
+        assert s1["jit_launches"] > s0["jit_launches"] and s1["interpreter_launches"] > s0["interpreter_launches"]
+        np.testing.assert_allclose(states[2], states[0], rtol=0, atol=1e-12)
+    finally:
+        plb.jit_set_mode(-1)
+
+
+@pytest.mark.gpu
+def test_jit_same_kernel_other_angles(plb, ref, jit_sync):
+    """Angles are run-time arguments: a second parameter set reuses the compiled kernels (no new compile)."""
+    n = 18
+    ops1, _ = circuits.strongly_entangling_layers(n, 2, 1)
+    ops2, _ = circuits.strongly_entangling_layers(n, 2, 2)
+    a = plb.StateVector(n)
+    a.apply_ops(ops1, fuse=True)
+    s1 = plb.jit_stats()
+    b = plb.StateVector(n)
+    b.apply_ops(ops2, fuse=True)
+    s2 = plb.jit_stats()
+    assert s2["compiled"] + s2["from_disk_cache"] == s1["compiled"] + s1["from_disk_cache"]
+    assert s2["jit_launches"] > s1["jit_launches"]
+    r = ref.StateVector(n)
+    r.apply_ops(ops2)
+    np.testing.assert_allclose(b.get_state(), r.get_state(), rtol=0, atol=1e-12)
