@@ -466,7 +466,10 @@ template <typename T2, class Cfg> class Gen {
     static int minb() {
         const char *e = std::getenv("PLB200_JIT_MINB");
         const int v = e ? std::atoi(e) : 0;
-        return v > 0 ? v : Cfg::MINB;
+        // measured on the 30-qubit benchmark tape: the specialised code wants 128 registers (no spills; ptxas
+        // takes 202 uncapped): c128 4 CTAs x 128 threads 211 ms (5: 232, 6: 282 with 0.5 KB of spills per
+        // thread), c64 2 CTAs x 256 threads 143 ms (3: 155, 4: 264)
+        return v > 0 ? v : (sizeof(T2) == 16 ? 4 : 2);
     }
 
   public:

@@ -15,6 +15,13 @@
 #include "DevTag.hpp"
 #include "Error.hpp"
 
+// tag types of core/utils/Memory.hpp, declared here so that this header also builds outside the reference tree
+namespace Pennylane::Util::MemoryStorageLocation {
+struct Internal;
+struct External;
+struct Undefined;
+} // namespace Pennylane::Util::MemoryStorageLocation
+
 namespace Pennylane::LightningB200 {
 
 namespace detail {
@@ -73,6 +80,9 @@ struct OpsBlob {
 template <class Precision = double> class StateVectorB200 {
   public:
     using PrecisionT = Precision;
+    // where the amplitudes live, as the reference's templates ask (core/utils/Memory.hpp:191-208;
+    // MeasurementsBase.hpp:291,485 branch on it): device memory owned by the engine = "Undefined", like LGPU
+    using MemoryStorageT = Pennylane::Util::MemoryStorageLocation::Undefined;
     using ComplexT = std::complex<PrecisionT>;
     using CFP_t = ComplexT; // device elements are layout-compatible interleaved (re, im)
 
