@@ -546,7 +546,21 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             {
                 uint32_t basis[4] = {0, 0, 0, 0}; // reduced basis by leading bit
                 std::vector<char> taken(M, 0);
+                // First and last round of a pass: when no register bit sits among the tile's LOW contiguous
+                // bits, those become the lowest lane bits (their swizzle columns are the unit vectors, so the
+                // shared accesses stay conflict-free): 2^LOW consecutive lanes then cover one 128-byte line and
+                // a specialised kernel (jit_codegen.hpp) moves that round's registers straight from / to
+                // global memory.
+                static_assert(SB == LOW, "the contiguous tile bits are the bank-group bits");
+                const bool edge_round = (r == 0 || r + 1 == hp.rounds.size()) && Cfg::NS == 1;
+                if (edge_round && (rmask_l & ((1u << LOW) - 1u)) == 0) {
+                    for (int i = 0; i < LOW; i++) {
+                        tpos.push_back(i), taken[i] = 1;
+                        basis[i] = 1u << i;
+                    }
+                }
                 for (int cand : nr) {
+                    if (taken[cand]) continue;
                     if (static_cast<int>(tpos.size()) == SB) break;
                     uint32_t c = col_of(cand);
                     for (int b = SB - 1; b >= 0 && c; b--)

@@ -17,6 +17,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -78,6 +79,42 @@ static_assert(sizeof(TileOp) == PLB_SIZEOF_TILEOP, "TileOp layout");
 static_assert(sizeof(PassParams) == PLB_SIZEOF_PASSPARAMS, "PassParams layout");
 static_assert(sizeof(PassHdr) + PLB_MAXROUNDS * sizeof(RoundHdr) == PLB_OFFSETOF_OPS, "PassParams layout");
 
+#if !PLB_DOUBLE && !defined(PLB_JIT_HOST) && !PLB_NO_FFMA2
+// c64 on the device: packed FP32 pairs.  sm_100a's FFMA2 / FMUL2 / FADD2 act on an (x, y) register pair with
+// free operand modifiers — broadcast of one scalar to both halves, half swap (LO_HI) and per-half negation —
+// which is exactly the shape of complex arithmetic: a shear is ONE instruction per amplitude instead of two,
+// a phase multiplication two instead of four.
+DEV T2 f2(real x, real y) { T2 r; r.x = x; r.y = y; return r; }
+DEV void cmul_ip(T2 &v, const T2 d) {
+    const T2 t = __fmul2_rn(f2(-v.y, v.x), f2(d.y, d.y));
+    v = __ffma2_rn(v, f2(d.x, d.x), t);
+}
+DEV void cshear_ip(T2 &a, const T2 t, const T2 &b) {
+    a = __ffma2_rn(f2(t.x, t.x), b, a);
+    a = __ffma2_rn(f2(-t.y, t.y), f2(b.y, b.x), a);
+}
+DEV void cswap(T2 &a, T2 &b) { const T2 t = a; a = b; b = t; }
+DEV void lift_r(T2 &a, T2 &b, const T2 m) {
+    a = __ffma2_rn(f2(m.x, m.x), b, a);
+    b = __ffma2_rn(f2(m.y, m.y), a, b);
+    a = __ffma2_rn(f2(m.x, m.x), b, a);
+}
+DEV void lift_i(T2 &a, T2 &b, const T2 m) {
+    a = __ffma2_rn(f2(-m.x, m.x), f2(b.y, b.x), a);
+    b = __ffma2_rn(f2(-m.y, m.y), f2(a.y, a.x), b);
+    a = __ffma2_rn(f2(-m.x, m.x), f2(b.y, b.x), a);
+}
+DEV void had(T2 &a, T2 &b) {
+    a = __fadd2_rn(a, b);
+    b = __ffma2_rn(f2((real)-2, (real)-2), b, a);
+}
+DEV void lu_r(T2 &a, T2 &b, const T2 m0, const T2 m1) {
+    a = __ffma2_rn(f2(m0.x, m0.x), b, a);
+    b = __ffma2_rn(f2(m0.y, m0.y), a, b);
+    a = __fmul2_rn(a, f2(m1.x, m1.x));
+    b = __fmul2_rn(b, f2(m1.y, m1.y));
+}
+#else
 DEV void cmul_ip(T2 &v, const T2 d) {
     const real t = v.x * d.y;
     v.x = v.x * d.x;
@@ -111,6 +148,7 @@ DEV void lu_r(T2 &a, T2 &b, const T2 m0, const T2 m1) {
     a.x = a.x * m1.x, a.y = a.y * m1.x;
     b.x = b.x * m1.y, b.y = b.y * m1.y;
 }
+#endif
 DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) {
     cshear_ip(a, m0, b);
     cshear_ip(b, m1, a);
@@ -165,49 +203,6 @@ DEV void store_tile(u32 tid, u64 base, const u64 *goff, T2 *__restrict__ sv, con
 )PLB";
 }
 
-inline const char *kernel_text() {
-    return R"PLB(
-#if defined(PLB_JIT_HOST)
-// test-only: the generated per-thread code run thread by thread on host memory (rounds are separated
-// by barriers on the device, so each phase is completed for every thread before the next starts)
-extern "C" void plb_pass_host(T2 *sv, const PassParams *ppp) {
-    const PassParams &pp = *ppp;
-    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)];
-    static u64 goff[1 << (PLB_M - PLB_LOW)];
-    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);
-    for (u64 t = 0; t < pp.hdr.ntiles; t++) {
-        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);
-        for (u32 tid = 0; tid < PLB_NT; tid++) load_tile(tid, base, goff, sv, smem);
-        PLB_HOST_ROUNDS
-        for (u32 tid = 0; tid < PLB_NT; tid++) store_tile(tid, base, goff, sv, smem);
-    }
-}
-#else
-extern "C" __global__ void __launch_bounds__(PLB_NT, PLB_MINB)
-    plb_pass(T2 *__restrict__ sv, const __grid_constant__ PassParams pp) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    u64 *goff = (u64 *)(smem + (sizeof(T2) << PLB_M));
-    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);
-    __syncthreads();
-    const u32 tid = threadIdx.x;
-    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
-        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);
-        if (t + gridDim.x < pp.hdr.ntiles) {
-            const u64 nbase = insert_bits_m(t + gridDim.x, pp.hdr.tile_ins);
-            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(sv + (nbase | goff[l])));
-        }
-        load_tile(tid, base, goff, sv, smem);
-        __syncthreads();
-        PLB_DEVICE_ROUNDS
-        store_tile(tid, base, goff, sv, smem);
-        __syncthreads();
-    }
-}
-#endif
-)PLB";
-}
-
 template <typename T2, class Cfg> class Gen {
     static constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NV = 1 << R, NTB = M - R;
     const PassParams<T2> &pp;
@@ -251,14 +246,32 @@ template <typename T2, class Cfg> class Gen {
         return "(((" + p + ") & 1) != 0)";
     }
 
-    void gen_round(int r) {
+    // local tile-bit positions of the thread bits / register bits of a round, recovered from the encoded
+    // shared-memory offsets (the swizzle only touches the bank-group bits, so the top set bit is the position)
+    static int top_bit(uint32_t v) { return 31 - __builtin_clz(v); }
+    void round_bits(const RoundHdr &rh, int tpos[NTB], int rl[R]) const {
+        for (int i = 0; i < NTB; i++) tpos[i] = top_bit(rh.w[i] / static_cast<uint32_t>(sizeof(T2)));
+        for (int i = 0; i < R; i++) rl[i] = top_bit(rh.sroff[1 << i] / static_cast<uint32_t>(sizeof(T2)));
+    }
+    // A round can exchange its registers with GLOBAL memory directly (no staging through shared memory, no
+    // barrier) when the lowest LOW lane bits are the tile's LOW contiguous bits: every 2^LOW lanes then cover one
+    // full 128-byte line per access.  The scheduler arranges that for the first and the last round of a pass
+    // whenever none of those bits is a register bit (fusion.cu, thread-bit assignment).
+    bool direct_ok(int r) const {
+        if (std::getenv("PLB200_JIT_NO_DIRECT")) return false;
+        int tpos[NTB], rl[R];
+        round_bits(pp.rounds[r], tpos, rl);
+        for (int i = 0; i < LOW; i++)
+            if (tpos[i] != i) return false;
+        return true;
+    }
+
+    // from_global / to_global: the round's registers come from / go to the state vector instead of the tile
+    void gen_round(int r, bool from_global, bool to_global) {
         const RoundHdr &rh = pp.rounds[r];
-        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem) {\n", r);
-        // thread part of the swizzled offset
-        s += "    const u32 sb = 0u";
-        for (int i = 0; i < NTB; i++) add(" ^ ((tid >> %d & 1u) * %s)", i, hex(rh.w[i]).c_str());
-        s += ";\n";
-        // register loads: the swizzle only mixes into the bank-group bits, everything above is a plain offset
+        int tpos[NTB], rl[R];
+        round_bits(rh, tpos, rl);
+        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, T2 *__restrict__ sv) {\n", r);
         const uint32_t lowmask = ((1u << Swz<T2>::B) - 1u) * static_cast<uint32_t>(sizeof(T2));
         std::vector<uint32_t> lows;
         auto low_id = [&](uint32_t low) {
@@ -267,12 +280,34 @@ template <typename T2, class Cfg> class Gen {
             lows.push_back(low);
             return static_cast<int>(lows.size() - 1);
         };
-        for (int u = 0; u < NV; u++) low_id(rh.sroff[u] & lowmask);
-        for (size_t i = 0; i < lows.size(); i++)
-            add("    unsigned char *const b%zu = smem + (sb ^ %s);\n", i, hex(lows[i]).c_str());
+        if (!from_global || !to_global) {
+            // thread part of the swizzled offset; the swizzle only mixes into the bank-group bits, everything
+            // above is a plain (immediate) offset
+            s += "    const u32 sb = 0u";
+            for (int i = 0; i < NTB; i++) add(" ^ ((tid >> %d & 1u) * %s)", i, hex(rh.w[i]).c_str());
+            s += ";\n";
+            for (int u = 0; u < NV; u++) low_id(rh.sroff[u] & lowmask);
+            for (size_t i = 0; i < lows.size(); i++)
+                add("    unsigned char *const b%zu = smem + (sb ^ %s);\n", i, hex(lows[i]).c_str());
+        }
+        if (from_global || to_global) {
+            // element offset of this thread inside the tile (global index bits) and of each register
+            s += "    const u64 goff_t = 0ull";
+            for (int i = 0; i < NTB; i++) add(" | ((tid >> %d & 1u) ? pp.hdr.tile_ins.lowmask[%d] + 1ull : 0ull)", i, tpos[i]);
+            s += ";\n    T2 *__restrict__ const gp = sv + (base | goff_t);\n";
+            for (int i = 0; i < R; i++) add("    const u64 ro%d = pp.hdr.tile_ins.lowmask[%d] + 1ull;\n", i, rl[i]);
+        }
+        auto greg = [&](int u) {
+            std::string e;
+            for (int i = 0; i < R; i++)
+                if ((u >> i) & 1) e += (e.empty() ? "ro" : " | ro") + std::to_string(i);
+            return e.empty() ? std::string("0ull") : "(" + e + ")";
+        };
         for (int u = 0; u < NV; u++) {
             perm[u] = u;
-            add("    T2 v%d = *(const T2 *)(b%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
+            if (from_global) add("    T2 v%d = gp[%s];\n", u, greg(u).c_str());
+            else
+                add("    T2 v%d = *(const T2 *)(b%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
         }
         // thread-scalar diagonal factors of this round (K_DIAG_T / K_DIAG1_T): merged when there are >= 2
         int n_tscalar = 0;
@@ -291,8 +326,11 @@ template <typename T2, class Cfg> class Gen {
             s += "    }\n";
         }
         gen_ladders(rh);
-        for (int u = 0; u < NV; u++)
-            add("    *(T2 *)(b%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), V(u).c_str());
+        for (int u = 0; u < NV; u++) {
+            if (to_global) add("    gp[%s] = %s;\n", greg(u).c_str(), V(u).c_str());
+            else
+                add("    *(T2 *)(b%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), V(u).c_str());
+        }
         s += "}\n";
     }
 
@@ -469,7 +507,7 @@ template <typename T2, class Cfg> class Gen {
         // measured on the 30-qubit benchmark tape: the specialised code wants 128 registers (no spills; ptxas
         // takes 202 uncapped): c128 4 CTAs x 128 threads 211 ms (5: 232, 6: 282 with 0.5 KB of spills per
         // thread), c64 2 CTAs x 256 threads 143 ms (3: 155, 4: 264)
-        return v > 0 ? v : (sizeof(T2) == 16 ? 4 : 2);
+        return v > 0 ? v : std::max(1, 512 / (1 << NTB));
     }
 
   public:
@@ -480,19 +518,58 @@ template <typename T2, class Cfg> class Gen {
         constexpr bool dbl = sizeof(T2) == 16;
         add("#define PLB_DOUBLE %d\n#define PLB_M %d\n#define PLB_LOW %d\n#define PLB_R %d\n#define PLB_NT %d\n#define PLB_MINB %d\n",
             dbl ? 1 : 0, M, LOW, R, 1 << NTB, minb());
+        add("#define PLB_NO_FFMA2 %d\n", std::getenv("PLB200_JIT_NO_FFMA2") ? 1 : 0);
         add("#define PLB_MAXROUNDS %d\n#define PLB_MAXOPS %d\n#define PLB_SWZ_B %d\n#define PLB_SWZ_COLS 0x%llxull\n", kMaxPassRounds,
             kMaxPassOps, Swz<T2>::B, static_cast<unsigned long long>(Swz<T2>::cols));
         add("#define PLB_SIZEOF_TILEOP %zu\n#define PLB_SIZEOF_PASSPARAMS %zu\n#define PLB_OFFSETOF_OPS %zu\n", sizeof(TileOp<T2>),
             sizeof(PassParams<T2>), offsetof(PassParams<T2>, ops));
         s += prelude();
-        for (int r = 0; r < pp.hdr.nrounds; r++) gen_round(r);
+        const int nr = pp.hdr.nrounds;
+        const bool first_direct = direct_ok(0), last_direct = direct_ok(nr - 1);
+        for (int r = 0; r < nr; r++) gen_round(r, r == 0 && first_direct, r == nr - 1 && last_direct);
+        // ---- the two drivers: the device kernel and the test-only host loop (phases separated by barriers on
+        // the device are completed for every thread before the next phase starts on the host)
         std::string dev, host;
-        for (int r = 0; r < pp.hdr.nrounds; r++) {
-            dev += "round_" + std::to_string(r) + "(pp, tid, base, smem); __syncthreads(); ";
-            host += "for (u32 tid = 0; tid < PLB_NT; tid++) round_" + std::to_string(r) + "(pp, tid, base, smem); ";
+        auto phase = [&](const std::string &call, bool barrier) {
+            dev += "        " + call + ";" + (barrier ? " __syncthreads();" : "") + "\n";
+            host += "        for (u32 tid = 0; tid < PLB_NT; tid++) { " + call + "; }\n";
+        };
+        // smem of the previous tile is still being read by the slower warps' last phase
+        if ((first_direct || last_direct) && nr > 1) dev += "        __syncthreads();\n";
+        if (!first_direct) phase("load_tile(tid, base, goff, sv, smem)", true);
+        for (int r = 0; r < nr; r++) {
+            const bool to_g = r == nr - 1 && last_direct;
+            phase("round_" + std::to_string(r) + "(pp, tid, base, smem, sv)", !to_g);
         }
-        s += "#define PLB_DEVICE_ROUNDS " + dev + "\n#define PLB_HOST_ROUNDS " + host + "\n";
-        s += kernel_text();
+        if (!last_direct) phase("store_tile(tid, base, goff, sv, smem)", !first_direct || nr == 1);
+        s += "#if defined(PLB_JIT_HOST)\n"
+             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp) {\n"
+             "    const PassParams &pp = *ppp;\n"
+             "    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)];\n"
+             "    static u64 goff[1 << (PLB_M - PLB_LOW)];\n"
+             "    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);\n"
+             "    for (u64 t = 0; t < pp.hdr.ntiles; t++) {\n"
+             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n" +
+             host +
+             "    }\n}\n"
+             "#else\n"
+             "extern \"C\" __global__ void __launch_bounds__(PLB_NT, PLB_MINB)\n"
+             "    plb_pass(T2 *__restrict__ sv, const __grid_constant__ PassParams pp) {\n"
+             "    extern __shared__ __align__(16) unsigned char smem[];\n"
+             "    u64 *goff = (u64 *)(smem + (sizeof(T2) << PLB_M));\n"
+             "    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);\n"
+             "    __syncthreads();\n"
+             "    const u32 tid = threadIdx.x;\n"
+             "    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {\n"
+             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n"
+             "        if (t + gridDim.x < pp.hdr.ntiles) {\n"
+             "            const u64 nbase = insert_bits_m(t + gridDim.x, pp.hdr.tile_ins);\n"
+             "            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT)\n"
+             "                asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(sv + (nbase | goff[l])));\n"
+             "        }\n" +
+             dev +
+             "    }\n}\n"
+             "#endif\n";
         return s;
     }
 };

@@ -10,7 +10,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 dtype = np.complex128 if (len(sys.argv) < 3 or sys.argv[2] == "c128") else np.complex64
 fuse = not (len(sys.argv) > 3 and sys.argv[3] == "nofuse")
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-ops = circuits.random_circuit(n, 20, 1234)
+kind = os.environ.get("PLB200_PROF_TAPE", "random")
+if kind == "light":   # one pass, one round, four cheap gates: the memory floor of the pass kernel
+    ops = [circuits.op("RX", [w], [0.3 + w]) for w in (3, 9, 14, 20)]
+elif kind == "light2":  # two rounds
+    ops = [circuits.op("RX", [w], [0.3 + w]) for w in (3, 5, 7, 9, 11, 13, 15, 17)]
+else:
+    ops = circuits.random_circuit(n, 20, 1234)
 sv = plb.StateVector(n, dtype, 0, torch.cuda.current_stream().cuda_stream)
 blob = plb.OpsBlob(ops)
 for _ in range(2):
