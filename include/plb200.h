@@ -238,6 +238,20 @@ int plb200_sv_swap_bits_peer(plb200_sv *sv, const int64_t *bits, int64_t k, int6
 /* CUDA IPC plumbing for the peer path (one process per GPU): export the slab of `sv` as a 64-byte
  * handle, map a peer's slab into this process (peer access over NVLink is enabled lazily), unmap. */
 int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64);
+/* Routed tape ("swap-out"): like plb200_sv_apply_ops(fuse = 1), but the LAST fused pass stores every amplitude
+ * where it belongs after exchanging the k local index bits lbits[] with k global (rank) bits — into this rank's
+ * own ping-pong slab, or straight into a peer's ping-pong slab over NVLink peer memory — so that the index-bit
+ * swap rides on the pass's store phase instead of costing a sweep of its own (replaces the swap — apply — swap
+ * sequence of StateVectorCudaMPI.hpp:1936-2243 and swapGlobalLocalWires, StateVectorKokkosMPI.hpp:747-889).
+ * dst[p] (p = value of the swapped LOCAL bits, bit i <-> lbits[i]) = peer-mapped ping-pong slab of the rank whose
+ * swapped global bits read p; dst[my_value] is ignored (own slab).  *routed = 1: the state now lives in the
+ * ping-pong slabs (every rank must synchronise before reading); 0: the tape was applied in place and the caller
+ * swaps with plb200_sv_swap_bit[s]_peer.  plb200_sv_alloc_alt allocates the second slab (same size). */
+int plb200_sv_alloc_alt(plb200_sv *sv);
+void *plb200_sv_alt_ptr(const plb200_sv *sv);
+int plb200_sv_ipc_handle_alt(const plb200_sv *sv, unsigned char *handle64);
+int plb200_sv_apply_ops_route(plb200_sv *sv, const plb200_ops_t *ops, int64_t k, const int64_t *lbits,
+                              int64_t my_value, void *const *dst, int *routed);
 int plb200_ipc_open(const unsigned char *handle64, int device, void **peer_ptr);
 int plb200_ipc_close(void *peer_ptr, int device);
 

@@ -70,6 +70,7 @@ struct StateVec {
     cudaStream_t stream = nullptr;
     void *data = nullptr;
     bool owned = true;
+    void *alt = nullptr; // ping-pong slab of the sharded mode's routed passes (same size as data), or null
     // scratch for reductions (partials + result), lazily allocated
     double *red = nullptr;
     size_t red_cap = 0;

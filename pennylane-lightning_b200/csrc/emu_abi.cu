@@ -16,6 +16,8 @@ int emulate_fused(int n, int precision, const std::vector<AdjItem> &items, bool 
 }
 
 namespace plb200 {
+int emulate_routed(int n, int precision, const std::vector<AdjItem> &items, bool scaled, void *sv0, const RouteSpec &rs,
+                   int (*standalone)(void *, int), void *ctx);
 void emu_kind_hist(int64_t out[32], bool reset);
 int64_t emu_jit_passes();
 void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]);
@@ -222,6 +224,35 @@ int plb200_emu_apply_ops(int64_t n, int precision, const plb200_ops_t *ops, void
         // the stand-alone accumulators are added after emulate_fused zeroes its own
         return emulate_fused(static_cast<int>(n), precision, items, false, scaled != 0, state, nullptr, &dummy, 0,
                              standalone_cb, &ctx, stats4);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Routed tape on host memory: like plb200_emu_apply_ops, but the last pass stores through the swap-out route
+// (dst[p]: host array receiving the amplitudes whose swapped local bits read p).  *routed as in
+// plb200_sv_apply_ops_route; when 0 the tape was applied to `state` in place.
+int plb200_emu_apply_ops_route(int64_t n, int precision, const plb200_ops_t *ops, void *state, int64_t k,
+                               const int64_t *lbits, int64_t my_value, void *const *dst, int *routed) {
+    try {
+        std::vector<AdjItem> items;
+        for (int64_t i = 0; i < ops->n_ops; i++)
+            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) {
+                AdjItem it;
+                it.op = std::move(lo);
+                items.push_back(std::move(it));
+            }
+        RouteSpec rs;
+        rs.k = static_cast<int>(k), rs.my_value = static_cast<int>(my_value);
+        for (int64_t i = 0; i < k; i++) rs.lbits[i] = static_cast<int>(lbits[i]);
+        for (int p = 0; p < (1 << k); p++) rs.dst[p] = dst[p];
+        double dummy = 0;
+        Ctx ctx{static_cast<int>(n), precision, &items, state, nullptr, &dummy};
+        const int r = emulate_routed(static_cast<int>(n), precision, items, true, state, rs, standalone_cb, &ctx);
+        if (r < 0) return 1;
+        *routed = r;
+        return 0;
     } catch (const std::exception &e) {
         g_err = e.what();
         return 1;

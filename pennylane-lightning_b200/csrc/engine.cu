@@ -92,6 +92,8 @@ void init_sv(StateVec &s, int64_t n, int precision, int device, void *stream, vo
 void free_sv(StateVec &s) {
     cudaSetDevice(s.device);
     if (s.owned && s.data) cudaFree(s.data);
+    if (s.alt) cudaFree(s.alt);
+    s.alt = nullptr;
     if (s.red) cudaFree(s.red);
     if (s.tbl) cudaFree(s.tbl);
     if (s.plan) cudaFree(s.plan);
@@ -571,6 +573,52 @@ int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse) {
     s.last_stats[1] = s.launches - before;
     ABI_CATCH
 }
+// ---- routed tape (sharded mode): the last pass stores through an index-bit swap into ping-pong slabs
+int plb200_sv_alloc_alt(plb200_sv *sv) {
+    ABI_TRY
+    StateVec &s = sv->s;
+    PLB_CHECK(s.owned, "a state vector on caller-owned memory cannot allocate a ping-pong slab");
+    s.set_device();
+    if (!s.alt) PLB_CUDA(cudaMalloc(&s.alt, s.bytes()));
+    ABI_CATCH
+}
+void *plb200_sv_alt_ptr(const plb200_sv *sv) { return sv->s.alt; }
+int plb200_sv_apply_ops_route(plb200_sv *sv, const plb200_ops_t *ops, int64_t k, const int64_t *lbits, int64_t my_value,
+                              void *const *dst, int *routed) {
+    ABI_TRY
+    StateVec &s = sv->s;
+    PLB_CHECK(k >= 1 && k <= 3, "Invalid number of bits");
+    PLB_CHECK(s.alt != nullptr, "plb200_sv_alloc_alt must be called first");
+    PLB_CHECK(my_value >= 0 && my_value < (int64_t{1} << k), "Invalid rank value");
+    RouteSpec rs;
+    rs.k = static_cast<int>(k);
+    rs.my_value = static_cast<int>(my_value);
+    uint64_t seen = 0;
+    for (int64_t i = 0; i < k; i++) {
+        PLB_CHECK(lbits[i] >= 0 && lbits[i] < s.n && !((seen >> lbits[i]) & 1), "Invalid bit");
+        seen |= uint64_t{1} << lbits[i];
+        rs.lbits[i] = static_cast<int>(lbits[i]);
+    }
+    for (int p = 0; p < (1 << k); p++) {
+        rs.dst[p] = p == my_value ? s.alt : dst[p];
+        PLB_CHECK(rs.dst[p] != nullptr, "missing destination slab");
+    }
+    std::vector<COp> all;
+    for (int64_t i = 0; i < ops->n_ops; i++) {
+        auto l = lower_gate(s.n, call_from_blob(*ops, i));
+        all.insert(all.end(), std::make_move_iterator(l.begin()), std::make_move_iterator(l.end()));
+    }
+    const int64_t before = s.launches;
+    const bool r = run_fused_routed(s, all, rs);
+    s.last_stats[0] = ops->n_ops;
+    s.last_stats[1] = s.launches - before;
+    // the routed pass wrote this rank's share into its own alt slab (and the peers write theirs into it):
+    // from here on that slab is the state
+    if (r) std::swap(s.data, s.alt);
+    *routed = r ? 1 : 0;
+    ABI_CATCH
+}
+
 int plb200_schedule_stats(int64_t n, int precision, const plb200_ops_t *ops, int64_t *out4) {
     ABI_TRY
     std::vector<COp> all;
@@ -967,6 +1015,15 @@ int plb200_sv_swap_bits_peer(plb200_sv *sv, const int64_t *bits, int64_t k, int6
     ABI_CATCH
 }
 
+int plb200_sv_ipc_handle_alt(const plb200_sv *sv, unsigned char *handle64) {
+    ABI_TRY
+    PLB_CHECK(sv->s.alt != nullptr, "no ping-pong slab");
+    sv->s.set_device();
+    cudaIpcMemHandle_t h;
+    PLB_CUDA(cudaIpcGetMemHandle(&h, sv->s.alt));
+    std::memcpy(handle64, &h, 64);
+    ABI_CATCH
+}
 int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64) {
     ABI_TRY
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

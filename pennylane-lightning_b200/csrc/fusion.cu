@@ -113,12 +113,14 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
 // Test-only (PLB200_EMU_JIT=1): the SPECIALISED source of the pass (jit_codegen.hpp) compiled with g++ under
 // -DPLB_JIT_HOST and run thread by thread on host memory, instead of the interpreter.
 int64_t g_emu_jit_passes = 0;
-template <typename T2, class Cfg> bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp) {
+template <typename T2, class Cfg>
+bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp, const jit::Route &route = jit::Route{},
+                      const jit::RouteParams<T2> *rp = nullptr) {
     if constexpr (Cfg::NS != 1) return false;
     else {
-        const std::string src = jit::generate_pass_source<T2, Cfg>(pp);
+        const std::string src = jit::generate_pass_source<T2, Cfg>(pp, route);
         if (src.empty()) return false;
-        static std::map<uint64_t, void (*)(void *, const void *)> cache;
+        static std::map<uint64_t, void (*)(void *, const void *, const void *)> cache;
         const uint64_t key = jit::fnv1a(src) ^ (static_cast<uint64_t>(src.size()) << 40);
         auto it = cache.find(key);
         if (it == cache.end()) {
@@ -134,7 +136,7 @@ template <typename T2, class Cfg> bool emulate_pass_jit(T2 *sv0, const PassParam
             if (std::system(cmd.c_str()) != 0) fail("emu jit: g++ failed on " + base + ".cpp");
             void *h = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
             if (!h) fail(std::string("emu jit: dlopen failed: ") + dlerror());
-            auto fn = reinterpret_cast<void (*)(void *, const void *)>(dlsym(h, "plb_pass_host"));
+            auto fn = reinterpret_cast<void (*)(void *, const void *, const void *)>(dlsym(h, "plb_pass_host"));
             if (!fn) fail("emu jit: plb_pass_host missing");
             it = cache.emplace(key, fn).first;
             if (!std::getenv("PLB200_EMU_JIT_KEEP")) {
@@ -142,7 +144,8 @@ template <typename T2, class Cfg> bool emulate_pass_jit(T2 *sv0, const PassParam
                 ::unlink((base + ".so").c_str());
             }
         }
-        it->second(sv0, &pp);
+        const jit::RouteParams<T2> none{};
+        it->second(sv0, &pp, rp ? rp : &none);
         g_emu_jit_passes++;
         return true;
     }
@@ -817,6 +820,24 @@ std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
     return items;
 }
 
+// Route description of the caller (engine.cu / the sharded driver): swap k local index bits `lbits` against k
+// global (rank) bits while the LAST pass of the tape stores its tile.
+template <typename T2> jit::Route tile_route(const RouteSpec &rs, const PassParams<T2> &pp, jit::RouteParams<T2> &rp) {
+    jit::Route r;
+    r.k = rs.k;
+    std::memset(&rp, 0, sizeof(rp));
+    for (int i = 0; i < rs.k; i++) {
+        r.loc[i] = -1;
+        for (int b = 0; b < pp.hdr.tile_ins.n; b++)
+            if (pp.hdr.tile_ins.lowmask[b] + 1 == (uint64_t{1} << rs.lbits[i])) r.loc[i] = b;
+        rp.lmask |= uint64_t{1} << rs.lbits[i];
+        if ((rs.my_value >> i) & 1) rp.rdep |= uint64_t{1} << rs.lbits[i];
+        rp.opos[i] = static_cast<uint32_t>(rs.lbits[i]);
+    }
+    for (int p = 0; p < (1 << rs.k); p++) rp.dst[p] = static_cast<T2 *>(rs.dst[p]);
+    return r;
+}
+
 #if !defined(PLB200_HOST_EMU)
 bool scaled_forms_enabled() {
     const char *e = std::getenv("PLB200_FUSE_SCALED");
@@ -890,6 +911,49 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
     }
+}
+
+// Forward tape whose last pass stores through a route.  Returns true when the final state went out through the
+// route (it then lives in the destination slabs), false when it stayed in place (no tile pass at the end of the
+// schedule, last round not line-coalesced, NVRTC missing): the caller then swaps with the stand-alone kernel.
+template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec &rs) {
+    using Cfg = FwdCfg<T2>;
+    const auto items = as_items(ops);
+    prepare_kernel<T2, Cfg>(sv.device);
+    const bool use_jit = jit::mode() != jit::Mode::Off && sv.n >= jit::min_qubits();
+    const unsigned nt = 1u << (Cfg::M - Cfg::R);
+    const size_t smem = smem_bytes_for<Cfg, T2>();
+    auto held = std::make_unique<PassParams<T2>>();
+    Step held_st;
+    bool have = false;
+    auto launch_plain = [&](const Step &st, const PassParams<T2> &pp) {
+        jit::Kernel k;
+        if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem);
+        if (k) jit::launch(k, st.grid, nt, smem, sv.stream, sv.data, &pp);
+        else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, pp);
+        sv.launches++;
+    };
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) {
+        if (have) launch_plain(held_st, *held), have = false; // the held pass was not the last step
+        if (st.op >= 0) launch_op(sv, ops[st.op]);
+        else if (st.op == -2) scale(sv, st.scale);
+        else {
+            std::memcpy(static_cast<void *>(held.get()), pp, sizeof(PassParams<T2>));
+            held_st = st, have = true;
+        }
+    });
+    if (!have) return false;
+    jit::RouteParams<T2> rp;
+    const jit::Route route = tile_route<T2>(rs, *held, rp);
+    jit::Kernel k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*held, route), sv.device, smem, /*force_sync=*/true);
+    if (!k) {
+        launch_plain(held_st, *held);
+        return false;
+    }
+    jit::launch(k, held_st.grid, nt, smem, sv.stream, sv.data, held.get(), &rp);
+    sv.launches++;
+    return true;
 }
 
 template <typename T2>
@@ -1013,6 +1077,15 @@ void run_fused(StateVec &sv, const std::vector<COp> &ops) {
     else run_fused_typed<float2>(sv, ops);
 }
 
+bool run_fused_routed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec &rs) {
+    sv.set_device();
+    if (sv.n < (sv.precision == 64 ? FwdCfg<double2>::M : FwdCfg<float2>::M) + 1 || ops.size() < 2 || !jit::available(nullptr)) {
+        run_fused(sv, ops);
+        return false;
+    }
+    return sv.precision == 64 ? run_fused_routed_typed<double2>(sv, ops, rs) : run_fused_routed_typed<float2>(sv, ops, rs);
+}
+
 void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
                        double *acc_host, int64_t stats[3]) {
     lambda.set_device();
@@ -1056,6 +1129,49 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
     });
     return rc;
+}
+// Test-only: a forward tape whose LAST pass stores through a route (the generated routed code on host memory);
+// returns 1 when routed, 0 when the tape was applied in place, < 0 on a stand-alone callback error.
+template <typename T2, class Cfg>
+int emulate_routed_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0, const RouteSpec &rs,
+                         int (*standalone)(void *, int), void *ctx) {
+    auto held = std::make_unique<PassParams<T2>>();
+    Step held_st;
+    bool have = false;
+    int rc = 0;
+    auto plain = [&](const Step &st, const PassParams<T2> &pp) {
+        std::vector<double> acc(kMaxPassOps, 0.0);
+        if (emulate_pass_jit<T2, Cfg>(sv0, pp)) return;
+        if (st.ext) emulate_pass<T2, Cfg, true>(sv0, nullptr, acc.data(), pp);
+        else emulate_pass<T2, Cfg, false>(sv0, nullptr, acc.data(), pp);
+    };
+    build_schedule<T2, Cfg>(n, 148, items, scaled, [&](const Step &st, const PassParams<T2> *pp) {
+        if (rc) return;
+        if (have) plain(held_st, *held), have = false;
+        if (st.op >= 0) rc = standalone(ctx, st.op);
+        else if (st.op == -2) {
+            for (uint64_t i = 0; i < (uint64_t{1} << n); i++) {
+                const cd v = cd(sv0[i].x, sv0[i].y) * st.scale;
+                sv0[i] = mk<T2>(v.real(), v.imag());
+            }
+        } else {
+            std::memcpy(static_cast<void *>(held.get()), pp, sizeof(PassParams<T2>));
+            held_st = st, have = true;
+        }
+    });
+    if (rc) return -1;
+    if (!have) return 0;
+    jit::RouteParams<T2> rp;
+    const jit::Route route = tile_route<T2>(rs, *held, rp);
+    if (emulate_pass_jit<T2, Cfg>(sv0, *held, route, &rp)) return 1;
+    plain(held_st, *held);
+    return 0;
+}
+int emulate_routed(int n, int precision, const std::vector<AdjItem> &items, bool scaled, void *sv0, const RouteSpec &rs,
+                   int (*standalone)(void *, int), void *ctx) {
+    if (precision == 64)
+        return emulate_routed_typed<double2, FwdCfg<double2>>(n, items, scaled, static_cast<double2 *>(sv0), rs, standalone, ctx);
+    return emulate_routed_typed<float2, FwdCfg<float2>>(n, items, scaled, static_cast<float2 *>(sv0), rs, standalone, ctx);
 }
 // schedule-only statistics of the adjoint sweep: {tile passes, stand-alone items, rounds, fused items}
 void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]) {

@@ -12,6 +12,19 @@ void run_fused(StateVec &sv, const std::vector<COp> &ops);
 // Host-only: out = {tile passes, stand-alone kernels, rounds, ops executed inside tile passes}
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]);
 
+// Swap-out route of the sharded mode: exchange the k local index bits `lbits` with k global (rank) bits while
+// the last pass of the tape stores its tiles.  dst[p] = slab that receives the amplitudes whose swapped local
+// bits read p (this rank's own ping-pong slab for p == my_value, a peer-mapped slab otherwise); my_value = this
+// rank's values of the swapped global bits.
+struct RouteSpec {
+    int k = 0;
+    int lbits[3] = {0, 0, 0};
+    int my_value = 0;
+    void *dst[8] = {nullptr};
+};
+// Applies the tape like run_fused(); returns true when the final state left through the route.
+bool run_fused_routed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec &rs);
+
 // Host-only: CUDA source of the specialised kernel of every tile pass of the tape (jit_codegen.hpp)
 void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector<std::string> &out);
 

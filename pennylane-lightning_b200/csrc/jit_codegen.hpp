@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -75,12 +76,13 @@ struct PLB_ALIGN(16) LadderEntry { u64 cmask_o; u32 cm_tid, pad; T2 ph; };
 struct PLB_ALIGN(16) RoundHdr { int first_op, nops, nlad, pad; u32 w[9]; u32 sroff[32]; };
 struct PLB_ALIGN(16) PassHdr { int nrounds, nops_total; u64 ntiles; int nslots, pad; BitInsert tile_ins; };
 struct PLB_ALIGN(16) PassParams { PassHdr hdr; RoundHdr rounds[PLB_MAXROUNDS]; TileOp ops[PLB_MAXOPS + 1]; };
+struct PLB_ALIGN(16) RouteParams { T2 *dst[8]; u64 lmask, rdep; u32 opos[4]; };
 static_assert(sizeof(TileOp) == PLB_SIZEOF_TILEOP, "TileOp layout");
 static_assert(sizeof(PassParams) == PLB_SIZEOF_PASSPARAMS, "PassParams layout");
 static_assert(sizeof(PassHdr) + PLB_MAXROUNDS * sizeof(RoundHdr) == PLB_OFFSETOF_OPS, "PassParams layout");
 
 #if !PLB_DOUBLE && !defined(PLB_JIT_HOST) && !PLB_NO_FFMA2
-// c64 on the device: packed FP32 pairs.  sm_100a's FFMA2 / FMUL2 / FADD2 act on an (x, y) register pair with
+// c64 on the device, opt-in (PLB200_JIT_FFMA2=1): packed FP32 pairs.  sm_100a's FFMA2 / FMUL2 / FADD2 act on an (x, y) register pair with
 // free operand modifiers — broadcast of one scalar to both halves, half swap (LO_HI) and per-half negation —
 // which is exactly the shape of complex arithmetic: a shear is ONE instruction per amplitude instead of two,
 // a phase multiplication two instead of four.
@@ -203,6 +205,23 @@ DEV void store_tile(u32 tid, u64 base, const u64 *goff, T2 *__restrict__ sv, con
 )PLB";
 }
 
+// Routed pass ("swap-out"): the LAST round of the pass stores every amplitude to the slab and position it has
+// AFTER an exchange of k local index bits with k global (rank) bits — its own ping-pong slab when the local
+// bits already equal this rank's global bits, otherwise straight into a peer's slab over NVLink.  The index-bit
+// swap of the sharded mode then costs no sweep of its own: the transfer rides on the pass's store phase.
+// loc[i]: tile-local position of swapped local bit i, or -1 when the bit lies outside the pass's tile.
+struct Route {
+    int k = 0;
+    int loc[3] = {-1, -1, -1};
+};
+// run-time half of a route (second kernel argument of a routed pass)
+template <typename T2> struct alignas(16) RouteParams {
+    T2 *dst[8];        // destination slab by the value of the swapped LOCAL bits (bit i <-> swapped bit i)
+    uint64_t lmask;    // the swapped local bits, as a mask over the slab index
+    uint64_t rdep;     // this rank's values of the swapped global bits, deposited at those positions
+    uint32_t opos[4];  // index-bit position of swapped bit i (used when it lies outside the tile)
+};
+
 template <typename T2, class Cfg> class Gen {
     static constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NV = 1 << R, NTB = M - R;
     const PassParams<T2> &pp;
@@ -260,18 +279,38 @@ template <typename T2, class Cfg> class Gen {
     bool direct_ok(int r) const {
         if (std::getenv("PLB200_JIT_NO_DIRECT")) return false;
         int tpos[NTB], rl[R];
-        round_bits(pp.rounds[r], tpos, rl);
+        round_bits(round_hdr(r), tpos, rl);
         for (int i = 0; i < LOW; i++)
             if (tpos[i] != i) return false;
         return true;
     }
 
     // from_global / to_global: the round's registers come from / go to the state vector instead of the tile
+    // round r of the pass; r == nrounds: the op-less TRANSFER round a routed pass appends when its last round is
+    // not line-coalesced (register bits = the highest tile bits; it replaces the store phase at the same cost)
+    RoundHdr transfer_round;
+    const RoundHdr &round_hdr(int r) const { return r < pp.hdr.nrounds ? pp.rounds[r] : transfer_round; }
+    void make_transfer_round() {
+        std::memset(&transfer_round, 0, sizeof(transfer_round));
+        int rl[R], tpos[NTB];
+        for (int i = 0; i < R; i++) rl[i] = M - R + i;
+        for (int i = 0; i < NTB; i++) tpos[i] = i;
+        for (int i = 0; i < NTB; i++) transfer_round.w[i] = swz<T2>(1u << tpos[i]) * static_cast<uint32_t>(sizeof(T2));
+        for (int u = 0; u < NV; u++) {
+            uint32_t o = 0;
+            for (int i = 0; i < R; i++)
+                if (u >> i & 1) o |= 1u << rl[i];
+            transfer_round.sroff[u] = swz<T2>(o) * static_cast<uint32_t>(sizeof(T2));
+        }
+    }
+
     void gen_round(int r, bool from_global, bool to_global) {
-        const RoundHdr &rh = pp.rounds[r];
+        const RoundHdr &rh = round_hdr(r);
         int tpos[NTB], rl[R];
         round_bits(rh, tpos, rl);
-        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, T2 *__restrict__ sv) {\n", r);
+        const bool routed = to_global && route.k > 0;
+        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, T2 *__restrict__ sv%s) {\n", r,
+            routed ? ", const RouteParams &rp" : "");
         const uint32_t lowmask = ((1u << Swz<T2>::B) - 1u) * static_cast<uint32_t>(sizeof(T2));
         std::vector<uint32_t> lows;
         auto low_id = [&](uint32_t low) {
@@ -326,8 +365,50 @@ template <typename T2, class Cfg> class Gen {
             s += "    }\n";
         }
         gen_ladders(rh);
+        // routed stores: swapped bit i of this amplitude selects the destination slab; inside the slab the
+        // swapped positions take this rank's global-bit values
+        int reg_of_swapped[3] = {-1, -1, -1};
+        if (routed) {
+            s += "    const u32 sel_t = 0u";
+            for (int i = 0; i < route.k; i++) {
+                const int lp = route.loc[i];
+                if (lp < 0) add(" | ((u32)((base >> rp.opos[%d]) & 1ull) << %d)", i, i);
+                else {
+                    int ti = -1;
+                    for (int j = 0; j < NTB; j++)
+                        if (tpos[j] == lp) ti = j;
+                    for (int j = 0; j < R; j++)
+                        if (rl[j] == lp) reg_of_swapped[i] = j;
+                    if (ti >= 0) add(" | ((tid >> %d & 1u) << %d)", ti, i);
+                }
+            }
+            s += ";\n    const u64 gb = ((base | goff_t) & ~rp.lmask) | rp.rdep;\n";
+            unsigned done = 0;
+            for (int u = 0; u < NV; u++) {
+                unsigned x = 0;
+                for (int i = 0; i < route.k; i++)
+                    if (reg_of_swapped[i] >= 0 && ((u >> reg_of_swapped[i]) & 1)) x |= 1u << i;
+                if (done >> x & 1u) continue;
+                done |= 1u << x;
+                add("    T2 *__restrict__ const d%u = rp.dst[sel_t | %uu] + gb;\n", x, x);
+            }
+        }
+        auto greg_routed = [&](int u) { // register part of the index without the swapped positions
+            std::string e;
+            for (int i = 0; i < R; i++) {
+                bool swapped = false;
+                for (int q = 0; q < route.k; q++) swapped = swapped || reg_of_swapped[q] == i;
+                if (((u >> i) & 1) && !swapped) e += (e.empty() ? "ro" : " | ro") + std::to_string(i);
+            }
+            return e.empty() ? std::string("0ull") : "(" + e + ")";
+        };
         for (int u = 0; u < NV; u++) {
-            if (to_global) add("    gp[%s] = %s;\n", greg(u).c_str(), V(u).c_str());
+            if (routed) {
+                unsigned x = 0;
+                for (int i = 0; i < route.k; i++)
+                    if (reg_of_swapped[i] >= 0 && ((u >> reg_of_swapped[i]) & 1)) x |= 1u << i;
+                add("    d%u[%s] = %s;\n", x, greg_routed(u).c_str(), V(u).c_str());
+            } else if (to_global) add("    gp[%s] = %s;\n", greg(u).c_str(), V(u).c_str());
             else
                 add("    *(T2 *)(b%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), V(u).c_str());
         }
@@ -512,20 +593,34 @@ template <typename T2, class Cfg> class Gen {
 
   public:
     bool ok = true;
-    explicit Gen(const PassParams<T2> &p) : pp(p) {}
+    Route route;
+    explicit Gen(const PassParams<T2> &p, const Route &rt = Route{}) : pp(p), route(rt) {}
 
     std::string run() {
         constexpr bool dbl = sizeof(T2) == 16;
         add("#define PLB_DOUBLE %d\n#define PLB_M %d\n#define PLB_LOW %d\n#define PLB_R %d\n#define PLB_NT %d\n#define PLB_MINB %d\n",
             dbl ? 1 : 0, M, LOW, R, 1 << NTB, minb());
-        add("#define PLB_NO_FFMA2 %d\n", std::getenv("PLB200_JIT_NO_FFMA2") ? 1 : 0);
+        // packed FP32 (FFMA2) is opt-in: measured SLOWER on the 30-qubit c64 tape (182 vs 124 ms): the 64-bit
+        // register-pair alignment of FFMA2 operands costs MOVs and spills that outweigh the halved FMA count
+        add("#define PLB_NO_FFMA2 %d\n", std::getenv("PLB200_JIT_FFMA2") ? 0 : 1);
         add("#define PLB_MAXROUNDS %d\n#define PLB_MAXOPS %d\n#define PLB_SWZ_B %d\n#define PLB_SWZ_COLS 0x%llxull\n", kMaxPassRounds,
             kMaxPassOps, Swz<T2>::B, static_cast<unsigned long long>(Swz<T2>::cols));
         add("#define PLB_SIZEOF_TILEOP %zu\n#define PLB_SIZEOF_PASSPARAMS %zu\n#define PLB_OFFSETOF_OPS %zu\n", sizeof(TileOp<T2>),
             sizeof(PassParams<T2>), offsetof(PassParams<T2>, ops));
         s += prelude();
-        const int nr = pp.hdr.nrounds;
-        const bool first_direct = direct_ok(0), last_direct = direct_ok(nr - 1);
+        int nr = pp.hdr.nrounds;
+        const bool first_direct = direct_ok(0);
+        bool last_direct = direct_ok(nr - 1);
+        if (route.k > 0 && !last_direct) {
+            // the routed store phase needs a line-coalesced last round: append the transfer round
+            make_transfer_round();
+            nr++;
+            last_direct = direct_ok(nr - 1);
+            if (!last_direct) {
+                ok = false;
+                return s;
+            }
+        }
         for (int r = 0; r < nr; r++) gen_round(r, r == 0 && first_direct, r == nr - 1 && last_direct);
         // ---- the two drivers: the device kernel and the test-only host loop (phases separated by barriers on
         // the device are completed for every thread before the next phase starts on the host)
@@ -539,12 +634,13 @@ template <typename T2, class Cfg> class Gen {
         if (!first_direct) phase("load_tile(tid, base, goff, sv, smem)", true);
         for (int r = 0; r < nr; r++) {
             const bool to_g = r == nr - 1 && last_direct;
-            phase("round_" + std::to_string(r) + "(pp, tid, base, smem, sv)", !to_g);
+            phase("round_" + std::to_string(r) + "(pp, tid, base, smem, sv" + (to_g && route.k > 0 ? ", rp)" : ")"), !to_g);
         }
         if (!last_direct) phase("store_tile(tid, base, goff, sv, smem)", !first_direct || nr == 1);
         s += "#if defined(PLB_JIT_HOST)\n"
-             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp) {\n"
+             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp, const RouteParams *rpp) {\n"
              "    const PassParams &pp = *ppp;\n"
+             "    const RouteParams &rp = *rpp; (void)rp;\n"
              "    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)];\n"
              "    static u64 goff[1 << (PLB_M - PLB_LOW)];\n"
              "    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);\n"
@@ -554,7 +650,8 @@ template <typename T2, class Cfg> class Gen {
              "    }\n}\n"
              "#else\n"
              "extern \"C\" __global__ void __launch_bounds__(PLB_NT, PLB_MINB)\n"
-             "    plb_pass(T2 *__restrict__ sv, const __grid_constant__ PassParams pp) {\n"
+             "    plb_pass(T2 *__restrict__ sv, const __grid_constant__ PassParams pp" +
+             std::string(route.k > 0 ? ", const __grid_constant__ RouteParams rp" : "") + ") {\n"
              "    extern __shared__ __align__(16) unsigned char smem[];\n"
              "    u64 *goff = (u64 *)(smem + (sizeof(T2) << PLB_M));\n"
              "    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);\n"
@@ -576,9 +673,10 @@ template <typename T2, class Cfg> class Gen {
 
 // Source of the specialised kernel of a forward pass, or "" when the pass holds an op kind the generator
 // does not cover (the interpreter kernel then runs it).
-template <typename T2, class Cfg> std::string generate_pass_source(const PassParams<T2> &pp) {
+template <typename T2, class Cfg>
+std::string generate_pass_source(const PassParams<T2> &pp, const Route &route = Route{}) {
     static_assert(Cfg::NS == 1, "forward passes only");
-    Gen<T2, Cfg> g(pp);
+    Gen<T2, Cfg> g(pp, route);
     std::string src = g.run();
     return g.ok ? src : std::string();
 }

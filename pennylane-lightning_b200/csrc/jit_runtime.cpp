@@ -301,9 +301,9 @@ bool available(std::string *why) {
     return true;
 }
 
-Kernel lookup(const std::string &src, int device, size_t smem_bytes) {
+Kernel lookup(const std::string &src, int device, size_t smem_bytes, bool force_sync) {
     Kernel k;
-    if (src.empty() || mode() == Mode::Off || !available(nullptr) || device < 0 || device >= 16) {
+    if (src.empty() || (mode() == Mode::Off && !force_sync) || !available(nullptr) || device < 0 || device >= 16) {
         g_stat_interp++;
         return k;
     }
@@ -313,10 +313,11 @@ Kernel lookup(const std::string &src, int device, size_t smem_bytes) {
     if (!slot) slot = std::make_unique<Entry>();
     Entry &e = *slot;
     e.seen++;
-    if (e.st == St::Seen && (mode() == Mode::Sync || e.seen >= 2)) {
+    const bool sync = force_sync || mode() == Mode::Sync;
+    if (e.st == St::Seen && (sync || e.seen >= 2)) {
         e.src = src;
         e.st = St::Queued;
-        if (mode() == Mode::Sync) {
+        if (sync) {
             lk.unlock();
             compile_entry(key);
             g_cv_idle.notify_all();
@@ -327,7 +328,7 @@ Kernel lookup(const std::string &src, int device, size_t smem_bytes) {
             g_cv_work.notify_one();
         }
     }
-    if (mode() == Mode::Sync && e.st == St::Queued) // another thread is compiling it
+    if (sync && e.st == St::Queued) // another thread (or a background worker) is compiling it
         g_cv_idle.wait(lk, [&] { return e.st != St::Queued; });
     if (e.st != St::Ready) {
         g_stat_interp++;
@@ -353,8 +354,9 @@ Kernel lookup(const std::string &src, int device, size_t smem_bytes) {
     return k;
 }
 
-void launch(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void *sv, const void *pass_params) {
-    void *args[2] = {&sv, const_cast<void *>(pass_params)};
+void launch(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void *sv, const void *pass_params,
+            const void *route_params) {
+    void *args[3] = {&sv, const_cast<void *>(pass_params), const_cast<void *>(route_params)};
     const int rc = driver().LaunchKernel(static_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, static_cast<unsigned>(smem_bytes),
                                          static_cast<CUstream>(stream), args, nullptr);
     if (rc != 0) fail("JIT pass kernel launch failed: " + cu_err(rc));

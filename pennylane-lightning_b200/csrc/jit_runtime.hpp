@@ -21,9 +21,10 @@ struct Kernel {
 };
 // The compiled kernel for this source on `device` (whose context must be current), or an empty handle when
 // it is not (yet) available — the caller then runs the interpreter kernel.
-Kernel lookup(const std::string &src, int device, size_t smem_bytes);
+// force_sync: compile now even in the background mode (routed passes have no interpreter equivalent)
+Kernel lookup(const std::string &src, int device, size_t smem_bytes, bool force_sync = false);
 void launch(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void *sv,
-            const void *pass_params);
+            const void *pass_params, const void *route_params = nullptr);
 void wait_idle();
 // {compiled, loaded from disk, launches of compiled kernels, launches left to the interpreter, failed,
 //  compile microseconds, queued + in flight, structures seen}

@@ -53,8 +53,11 @@ template <typename T2> struct FwdCfg;
 #ifndef PLB200_FWD128_MINB
 #define PLB200_FWD128_MINB 6 /* 80 registers, 24 warps/SM: measured 283 ms vs 314 (5) vs 319 (4) on the 30q tape */
 #endif
+#ifndef PLB200_FWD128_R
+#define PLB200_FWD128_R 4
+#endif
 template <> struct FwdCfg<double2> {
-    static constexpr int M = PLB200_FWD128_M, LOW = 3, R = 4, NS = 1, MINB = PLB200_FWD128_MINB;
+    static constexpr int M = PLB200_FWD128_M, LOW = 3, R = PLB200_FWD128_R, NS = 1, MINB = PLB200_FWD128_MINB;
 };
 #ifndef PLB200_FWD64_M
 #define PLB200_FWD64_M 13
@@ -62,8 +65,11 @@ template <> struct FwdCfg<double2> {
 #ifndef PLB200_FWD64_MINB
 #define PLB200_FWD64_MINB 3 /* 80 registers, 24 warps/SM: 176 ms vs 207 (2) on the 30q tape */
 #endif
+#ifndef PLB200_FWD64_R
+#define PLB200_FWD64_R 5
+#endif
 template <> struct FwdCfg<float2> {
-    static constexpr int M = PLB200_FWD64_M, LOW = 4, R = 5, NS = 1, MINB = PLB200_FWD64_MINB;
+    static constexpr int M = PLB200_FWD64_M, LOW = 4, R = PLB200_FWD64_R, NS = 1, MINB = PLB200_FWD64_MINB;
 };
 // adjoint pass: two states, 2 x 32 KiB tiles, 8 + 8 amplitudes per thread
 template <typename T2> struct AdjCfg;

@@ -109,7 +109,7 @@ class LocalEngine:
         _capi._check(_capi.lib().plb200_sv_ipc_handle(self.sv._h, buf))
         return bytes(buf)
 
-    def open_peer(self, rank, handle):
+    def open_peer(self, rank, handle, alt=False):
         import ctypes as C
 
         from . import _capi
@@ -117,7 +117,46 @@ class LocalEngine:
         ptr = C.c_void_p()
         buf = (C.c_ubyte * 64).from_buffer_copy(handle)
         _capi._check(_capi.lib().plb200_ipc_open(buf, self.device.index or 0, C.byref(ptr)))
-        self.peers[rank] = ptr.value
+        if alt:
+            if not hasattr(self, "peers_alt"):
+                self.peers_alt = {}
+            self.peers_alt[rank] = ptr.value
+        else:
+            self.peers[rank] = ptr.value
+
+    def flip_slabs(self):
+        """After a routed pass every rank's ping-pong slab is its state: the peer maps follow."""
+        self.peers, self.peers_alt = self.peers_alt, self.peers
+
+    # ---- ping-pong slab + routed tapes (the index-bit swap rides on the last pass's store phase)
+    def alloc_alt(self):
+        from . import _capi
+
+        _capi._check(_capi.lib().plb200_sv_alloc_alt(self.sv._h))
+
+    def ipc_handle_alt(self):
+        import ctypes as C
+
+        from . import _capi
+
+        buf = (C.c_ubyte * 64)()
+        _capi._check(_capi.lib().plb200_sv_ipc_handle_alt(self.sv._h, buf))
+        return bytes(buf)
+
+    def apply_ops_route(self, ops, lbits, my_value, dst_ptrs):
+        """Apply `ops`; the last fused pass stores through the swap of local bits `lbits` with the ranks' global
+        bits (dst_ptrs[p]: peer slab for local-bit value p).  Returns True when the state left through the route."""
+        import ctypes as C
+
+        from . import _capi
+
+        blob = _capi.OpsBlob(ops)
+        k = len(lbits)
+        arr = (C.c_void_p * (1 << k))(*[None if p == my_value else dst_ptrs[p] for p in range(1 << k)])
+        routed = C.c_int(0)
+        _capi._check(_capi.lib().plb200_sv_apply_ops_route(self.sv._h, blob.ptr(), C.c_int64(k), (C.c_int64 * k)(*lbits),
+                                                           C.c_int64(my_value), arr, C.byref(routed)))
+        return bool(routed.value)
 
     def close_peers(self):
         """Unmap the peers' slabs (their owners cannot release the memory while a mapping exists)."""
@@ -125,9 +164,11 @@ class LocalEngine:
 
         from . import _capi
 
-        for r, ptr in list(self.peers.items()):
-            _capi.lib().plb200_ipc_close(C.c_void_p(ptr), self.device.index or 0)
+        for ptrs in (self.peers, getattr(self, "peers_alt", {})):
+            for r, ptr in list(ptrs.items()):
+                _capi.lib().plb200_ipc_close(C.c_void_p(ptr), self.device.index or 0)
         self.peers = {}
+        self.peers_alt = {}
 
     def swap_bit_peer(self, bit, keep, partner, half):
         import ctypes as C
@@ -231,9 +272,27 @@ class DistStateVector:
             # run at 33 local qubits did not finish inside the round's remaining GPU budget, so the
             # chained single-bit swaps (measured at 36 qubits) stay the default until that is understood.
             self.multi_swap = os.environ.get("PLB200_SWAP_MULTI", "0") == "1"
+            # PLB200_SWAP_FUSED (default on when a second slab fits): the swap is folded into the store phase of
+            # the last pass before it (plb200_sv_apply_ops_route): amplitudes go straight to their owner's
+            # ping-pong slab over NVLink, no separate sweep.  Needs 2 x slab bytes of HBM per GPU.
+            self.fused_swap = False
+            if os.environ.get("PLB200_SWAP_FUSED", "1") != "0" and hasattr(self.engine, "alloc_alt"):
+                free, _ = torch.cuda.mem_get_info()
+                ok = torch.tensor([1.0 if (self.dtype.itemsize << self.nloc) * 1.05 < free else 0.0], device="cuda")
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                self.fused_swap = bool(ok.item() >= 1.0)
+            every = self.multi_swap or self.fused_swap
             for r in range(self.world):
-                if r != self.rank and (self.multi_swap or bin(r ^ self.rank).count("1") == 1):
+                if r != self.rank and (every or bin(r ^ self.rank).count("1") == 1):
                     self.engine.open_peer(r, handles[r])
+            if self.fused_swap:
+                self.engine.alloc_alt()
+                alt_handles = [None] * self.world
+                dist.all_gather_object(alt_handles, self.engine.ipc_handle_alt(), group=group)
+                for r in range(self.world):
+                    if r != self.rank:
+                        self.engine.open_peer(r, alt_handles[r], alt=True)
+            self.n_fused_swaps = 0
         self.reset()
 
     def close(self):
@@ -398,13 +457,18 @@ class DistStateVector:
                     m, w, cw, cv = payload
                     batch.append(dict(name="Matrix", wires=w, params=[], inverse=False, ctrl_wires=cw, ctrl_values=cv,
                                       matrix=m))
-            self.engine.apply_ops(batch, fuse=fuse)
-            if rest:
-                self._make_local(need, rest)
+            pairs = self._choose_pairs(need, rest) if rest else []
+            if pairs and fuse and getattr(self, "fused_swap", False) and len(pairs) <= 3 and len(batch) >= 2:
+                self._apply_and_swap_fused(batch, pairs)
+            else:
+                self.engine.apply_ops(batch, fuse=fuse)
+                if pairs:
+                    self._swap_pairs(pairs)
             pending = rest
 
-    def _make_local(self, need, rest):
-        """Swap the needed global wires in, evicting local wires with the farthest next non-diagonal use."""
+    def _choose_pairs(self, need, rest):
+        """(global wire, local wire) pairs to exchange: the needed global wires come in, the local wires with the
+        farthest next non-diagonal use go out.  Depends only on the tape and the wire map: same on every rank."""
         nxt = {}
         for i, op in enumerate(rest):
             for w in self._nondiag_targets(op):
@@ -415,13 +479,54 @@ class DistStateVector:
         # candidate): swapping a bit below the 128-B line splits every line (323 vs 692 GB/s measured)
         low = 3 if self.dtype == np.complex128 else 4
         cand.sort(key=lambda w: (self.phys[w] >= low, nxt.get(w, 1 << 30), self.phys[w]), reverse=True)
-        pairs = list(zip(need, cand))
+        return list(zip(need, cand))
+
+    def _swap_pairs(self, pairs):
         if (self.swap_mode == "peer" and getattr(self, "multi_swap", False) and 1 < len(pairs) <= 3
                 and hasattr(self.engine, "swap_bits_peer")):
             self._swap_multi(pairs)
         else:
             for gw, lw in pairs:
                 self._swap(gw, lw)
+
+    def _route_tables(self, pairs):
+        gbits = [self.phys[gw] for gw, _ in pairs]
+        lbits = [self.phys[lw] for _, lw in pairs]
+        k = len(pairs)
+        my_value = sum(((self.rank >> (gb - self.nloc)) & 1) << i for i, gb in enumerate(gbits))
+        partner_ranks = []
+        for p in range(1 << k):
+            r = self.rank
+            for i, gb in enumerate(gbits):
+                bit = 1 << (gb - self.nloc)
+                r = (r | bit) if (p >> i) & 1 else (r & ~bit)
+            partner_ranks.append(r)
+        return gbits, lbits, my_value, partner_ranks
+
+    def _apply_and_swap_fused(self, batch, pairs):
+        """The batch's last pass stores every amplitude into its owner's ping-pong slab (own or a peer's, over
+        NVLink peer memory): the exchange costs no sweep of its own.  Falls back to the stand-alone swap kernels
+        when the engine could not route (identical decision on every rank: it depends on the schedule only)."""
+        dist = self.dist
+        gbits, lbits, my_value, partner_ranks = self._route_tables(pairs)
+        dst = [None if p == my_value else self.engine.peers_alt[r] for p, r in enumerate(partner_ranks)]
+        routed = self.engine.apply_ops_route(batch, lbits, my_value, dst)
+        flag = self.torch.tensor([1.0 if routed else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # also the barrier: every rank's stores landed
+        if flag.item() < 1.0:
+            if routed:
+                raise RuntimeError("ranks disagree on routing a pass (schedules must be rank-independent)")
+            self._swap_pairs(pairs)
+            return
+        # flag.item() returned: every rank's routed kernel has completed (the reduction is stream-ordered after
+        # it on every rank), so all peer stores have landed
+        self.engine.flip_slabs()
+        for (gw, lw), gb, lb in zip(pairs, gbits, lbits):
+            self.phys[gw], self.phys[lw] = lb, gb
+        k = len(pairs)
+        self.n_swaps += k
+        self.n_fused_swaps += k
+        self.swap_bytes += ((1 << self.nloc) - (1 << (self.nloc - k))) * self.dtype.itemsize
 
     # ------------------------------------------------------------------ measurements
     def _allreduce(self, arr):

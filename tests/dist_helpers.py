@@ -103,9 +103,16 @@ def worker(rank, world, n, seed, port, backend, q, swap="auto"):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    if swap == "peer-multi":  # the opt-in k-bit all-to-all exchange
+    if swap == "peer-multi":  # the k-bit all-to-all exchange kernel, stand-alone (no routed passes)
         os.environ["PLB200_SWAP_MULTI"] = "1"
+        os.environ["PLB200_SWAP_FUSED"] = "0"
         swap = "peer"
+    elif swap == "peer-nofuse":  # chained single-bit exchange kernels
+        os.environ["PLB200_SWAP_FUSED"] = "0"
+        swap = "peer"
+    elif swap == "peer":  # default: the swap rides on the last pass's store phase (routed passes)
+        os.environ["PLB200_SWAP_MULTI"] = "1"
+        os.environ["PLB200_JIT_MIN_QUBITS"] = "12"
     dist.init_process_group(backend, rank=rank, world_size=world)
     from pennylane_lightning_b200.dist import DistStateVector
 
@@ -119,7 +126,8 @@ def worker(rank, world, n, seed, port, backend, q, swap="auto"):
         z = sv.expval_z_all()
         full = sv.gather_state()
         if rank == 0:
-            q.put(dict(state=full, z=z, norm2=sv.last_norm2, swaps=sv.n_swaps))
+            q.put(dict(state=full, z=z, norm2=sv.last_norm2, swaps=sv.n_swaps,
+                       fused_swaps=getattr(sv, "n_fused_swaps", 0)))
     finally:
         dist.destroy_process_group()
 

@@ -16,13 +16,13 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("swap", ["peer", "peer-multi", "nccl"])
+@pytest.mark.parametrize("swap", ["peer", "peer-nofuse", "peer-multi", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_gpu_matches_single_gpu_and_reference(plb, ref, world, swap):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     n, seed = 18, 10 + world
-    res = run_ranks(world, n, seed, "nccl", port=29700 + world + {"peer": 10, "peer-multi": 20, "nccl": 0}[swap], swap=swap)
+    res = run_ranks(world, n, seed, "nccl", port=29700 + world + {"peer": 10, "peer-multi": 20, "nccl": 0, "peer-nofuse": 30}[swap], swap=swap)
     ops = mixed_circuit(n, seed)
     single = plb.StateVector(n)
     single.apply_ops(ops, fuse=True)
@@ -32,3 +32,5 @@ def test_sharded_gpu_matches_single_gpu_and_reference(plb, ref, world, swap):
     np.testing.assert_allclose(res["state"], single.get_state(), rtol=0, atol=1e-12)
     assert abs(res["norm2"] - 1.0) < 1e-12
     assert res["swaps"] > 0
+    if swap == "peer":
+        assert res["fused_swaps"] > 0  # at least one exchange rode on a pass's store phase
