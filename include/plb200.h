@@ -216,6 +216,24 @@ int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, i
                             const plb200_ops_t *ops, const int64_t *trainable, int64_t n_tp,
                             int apply_ops, double *jac);
 
+/* SparseHamiltonian (core/observables/Observables.hpp:592-699; ObservablesGPU.hpp SparseHamiltonian): a CSR
+ * matrix over the full 2^n index space; data = nnz (re, im) pairs.  Applied with the engine's own CSR SpMV
+ * kernel (replaces cusparseSpMV, lightning_gpu/utils/LinearAlg.hpp:378-620). */
+int plb200_obs_sparse(plb200_obs **out, const int64_t *indptr, const int64_t *indices, const double *data,
+                      int64_t n_rows);
+/* Measurements::expval / var CSR overloads (lightning_gpu/bindings/LGPUBindings.hpp:65-150) */
+int plb200_expval_sparse(plb200_sv *sv, const int64_t *indptr, const int64_t *indices, const double *data,
+                         int64_t n_rows, double *out);
+int plb200_var_sparse(plb200_sv *sv, const int64_t *indptr, const int64_t *indices, const double *data,
+                      int64_t n_rows, double *out);
+/* Host-only Hermitian eigen-decomposition for HermitianObs measured with shots (replaces the scipy-openblas
+ * zheev of core/utils/UtilLinearAlg.hpp:59-117): eigvals ascending, unitary = V^dagger row-major (re, im). */
+int plb200_hermitian_eigh(const double *matrix, int64_t dim, double *eigvals, double *unitary);
+/* VectorJacobianProduct (lightning_qubit/algorithms/VectorJacobianProduct.hpp:43-163): dy = 2^n host complex
+ * pairs (cotangent of the state), out = n_tp complex pairs. */
+int plb200_vjp(const plb200_sv *sv, const double *dy, const plb200_ops_t *ops, const int64_t *trainable,
+               int64_t n_tp, int apply_ops, double *out);
+
 /* ------------------------------------------------------------------ distributed support
  * Local half of a global<->local index-bit swap (replaces custatevecSVSwapWorker /
  * StateVectorKokkosMPI::swapGlobalLocalWires, StateVectorKokkosMPI.hpp:747-889).

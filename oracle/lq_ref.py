@@ -146,6 +146,20 @@ class Observable:
         return cls(C.c_void_p(h), sfx)
 
     @classmethod
+    def sparse(cls, indptr, indices, data, wires, dtype=np.complex128):
+        sfx = "c128" if np.dtype(dtype) == np.complex128 else "c64"
+        ip, ipp = _i64(indptr)
+        ix, ixp = _i64(indices)
+        d, dp = _c128(data)
+        w, wp = _i64(wires)
+        f = getattr(lib(), f"lqref_obs_sparse_{sfx}")
+        f.restype = C.c_void_p
+        h = f(ipp, ixp, dp, C.c_int64(len(ip) - 1), wp, C.c_int64(len(w)))
+        if not h:
+            raise RefError(lib().lqref_last_error().decode())
+        return cls(C.c_void_p(h), sfx)
+
+    @classmethod
     def tensor(cls, terms):
         sfx = terms[0]._sfx
         arr = (C.c_void_p * len(terms))(*[t._h for t in terms])
@@ -330,6 +344,15 @@ class StateVector:
         out = np.empty((shots, k), dtype=np.uint64)
         _check(self._f("generate_samples")(self._h, wp, C.c_int64(nw), C.c_int64(shots), C.c_int64(seed),
                                            out.ctypes.data_as(_u64p)))
+        return out
+
+    def vjp(self, ops, dy, trainable, apply_ops=False):
+        blob = ops if isinstance(ops, OpsBlob) else OpsBlob(ops)
+        tp, tpp = _i64(trainable)
+        d, dp = _c128(dy)
+        out = np.zeros(len(tp), dtype=np.complex128)
+        _check(self._f("vjp")(self._h, dp, blob.ptr(), tpp, C.c_int64(len(tp)), int(bool(apply_ops)),
+                              out.ctypes.data_as(_f64p)))
         return out
 
     def adjoint_jacobian(self, observables, ops, trainable, apply_ops=False):

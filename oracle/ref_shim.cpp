@@ -25,6 +25,7 @@
 #include "MeasurementsLQubit.hpp"
 #include "ObservablesLQubit.hpp"
 #include "StateVectorLQubitManaged.hpp"
+#include "VectorJacobianProduct.hpp"
 
 using namespace Pennylane::LightningQubit;
 using namespace Pennylane::LightningQubit::Measures;
@@ -246,6 +247,24 @@ template <class T> OpsData<SV<T>> make_ops(const OpsBlob &b) {
             return nullptr;                                                    \
         }                                                                      \
     }                                                                          \
+    void *lqref_obs_sparse_##SFX(const int64_t *indptr, const int64_t *indices,\
+                                 const double *data, int64_t n_rows,           \
+                                 const int64_t *wires, int64_t nw) {           \
+        try {                                                                  \
+            using SH = SparseHamiltonian<SV<T>>;                               \
+            const int64_t nnz = indptr[n_rows];                                \
+            std::vector<std::complex<T>> d(nnz);                               \
+            for (int64_t k = 0; k < nnz; k++)                                  \
+                d[k] = {static_cast<T>(data[2 * k]),                           \
+                        static_cast<T>(data[2 * k + 1])};                      \
+            std::vector<typename SH::IdxT> ix(indices, indices + nnz),         \
+                ip(indptr, indptr + n_rows + 1);                               \
+            return new Obs<T>(std::make_shared<SH>(d, ix, ip, vec_sz(wires, nw)));\
+        } catch (const std::exception &e) {                                    \
+            g_err = e.what();                                                  \
+            return nullptr;                                                    \
+        }                                                                      \
+    }                                                                          \
     void lqref_obs_destroy_##SFX(void *o) { delete static_cast<Obs<T> *>(o); } \
     int lqref_obs_apply_##SFX(void *o, void *h) {                              \
         LQ_TRY(*static_cast<Obs<T> *>(o))                                      \
@@ -384,6 +403,24 @@ template <class T> OpsData<SV<T>> make_ops(const OpsBlob &b) {
         AdjointJacobian<SV<T>> adj;                                            \
         adj.adjointJacobian(std::span<T>{j}, jd, *sv, apply_ops != 0);         \
         for (std::size_t i = 0; i < j.size(); i++) jac[i] = j[i];              \
+        LQ_CATCH                                                               \
+    }                                                                          \
+    int lqref_vjp_##SFX(void *h, const double *dy, const OpsBlob *blob,        \
+                        const int64_t *tp, int64_t n_tp, int apply_ops,        \
+                        double *out) {                                         \
+        LQ_TRY auto *sv = static_cast<SV<T> *>(h);                             \
+        auto ops = make_ops<T>(*blob);                                         \
+        JacobianData<SV<T>> jd(ops.getTotalNumParams(), sv->getLength(),       \
+                               sv->getData(), {}, ops, vec_sz(tp, n_tp));      \
+        std::vector<std::complex<T>> d(sv->getLength()), j(n_tp);              \
+        for (std::size_t i = 0; i < d.size(); i++)                             \
+            d[i] = {static_cast<T>(dy[2 * i]), static_cast<T>(dy[2 * i + 1])}; \
+        Pennylane::LightningQubit::Algorithms::VectorJacobianProduct<SV<T>> v; \
+        v(std::span<std::complex<T>>{j},                                       \
+          jd, std::span<const std::complex<T>>{d.data(), d.size()},            \
+          apply_ops != 0);                                                     \
+        for (std::size_t i = 0; i < j.size(); i++)                             \
+            out[2 * i] = j[i].real(), out[2 * i + 1] = j[i].imag();            \
         LQ_CATCH                                                               \
     }                                                                          \
     }

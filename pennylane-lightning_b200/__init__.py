@@ -16,6 +16,7 @@ from ._capi import (  # noqa: F401
     OpsBlob,
     StateVector,
     build,
+    hermitian_eigh,
     jit_available,
     jit_enabled,
     jit_mode,

@@ -131,6 +131,17 @@ def jit_stats() -> dict:
     return dict(zip(keys, [int(x) for x in out]))
 
 
+def hermitian_eigh(matrix):
+    """Host eigen-decomposition of a Hermitian matrix -> (eigvals ascending, unitary = V^dagger)."""
+    m = np.ascontiguousarray(np.asarray(matrix, dtype=np.complex128))
+    dim = m.shape[0]
+    ev = np.empty(dim, dtype=np.float64)
+    u = np.empty((dim, dim), dtype=np.complex128)
+    _check(lib().plb200_hermitian_eigh(m.ctypes.data_as(_f64p), C.c_int64(dim), ev.ctypes.data_as(_f64p),
+                                       u.ctypes.data_as(_f64p)))
+    return ev, u
+
+
 class OpsBlob:
     """Flattened tape (plb200_ops_t): the C image of OpsData (JacobianData.hpp:39-253).
 
@@ -435,6 +446,22 @@ class StateVector:
                                                     out.ctypes.data_as(_f64p)))
         return out
 
+    def expval_sparse(self, indptr, indices, data):
+        ip, ipp = _i64(indptr)
+        ix, ixp = _i64(indices)
+        d, dp = _c128(data)
+        out = C.c_double()
+        _check(lib().plb200_expval_sparse(self._h, ipp, ixp, dp, C.c_int64(len(ip) - 1), C.byref(out)))
+        return out.value
+
+    def var_sparse(self, indptr, indices, data):
+        ip, ipp = _i64(indptr)
+        ix, ixp = _i64(indices)
+        d, dp = _c128(data)
+        out = C.c_double()
+        _check(lib().plb200_var_sparse(self._h, ipp, ixp, dp, C.c_int64(len(ip) - 1), C.byref(out)))
+        return out.value
+
     def expval(self, obs: Observable):
         out = C.c_double()
         _check(lib().plb200_expval_obs(self._h, obs._h, C.byref(out)))
@@ -457,6 +484,16 @@ class StateVector:
         out = np.empty((shots, k), dtype=np.uint64)
         _check(lib().plb200_generate_samples(self._h, wp, C.c_int64(nw), C.c_int64(shots), C.c_int64(seed),
                                              out.ctypes.data_as(_u64p)))
+        return out
+
+    def vjp(self, ops, dy, trainable, apply_ops=False):
+        """VectorJacobianProduct: vjp[k] = sum_i conj(dy_i) d psi_i / d theta_k (dy: 2^n complex cotangent)."""
+        blob = ops if isinstance(ops, OpsBlob) else OpsBlob(ops)
+        tp, tpp = _i64(trainable)
+        d, dp = _c128(dy)
+        out = np.zeros(len(tp), dtype=np.complex128)
+        _check(lib().plb200_vjp(self._h, dp, blob.ptr(), tpp, C.c_int64(len(tp)), int(bool(apply_ops)),
+                                out.ctypes.data_as(_f64p)))
         return out
 
     # ------------------------------------------------------------------ adjoint Jacobian

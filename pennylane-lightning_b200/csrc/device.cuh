@@ -110,6 +110,9 @@ double expval_matrix_small(StateVec &sv, const std::vector<cd> &matrix, const st
 // out = sum_k coeff_k P_k in   (Hamiltonian of Pauli words applied out-of-place)
 void pauli_sum_apply(StateVec &out, const StateVec &in, const PauliWordMask *words, const double *coeffs,
                      int64_t n_words);
+// out = A in, A in CSR over the full index space (device arrays; values complex128)
+void csr_apply(StateVec &out, const StateVec &in, const int64_t *d_indptr, const int64_t *d_indices, const void *d_vals,
+               int64_t nnz);
 void scatter_values(StateVec &sv, const int64_t *idx, const double *vals, int64_t n);
 void set_state_on_wires(StateVec &sv, const double *vals, const std::vector<int> &tbits);
 void collapse_zero(StateVec &sv, int bit, int keep_value);

@@ -24,7 +24,10 @@ struct plb200_sv {
 };
 
 struct plb200_obs {
-    enum Kind { NAMED, HERMITIAN, TENSOR, HAMILTONIAN } kind = NAMED;
+    enum Kind { NAMED, HERMITIAN, TENSOR, HAMILTONIAN, SPARSE } kind = NAMED;
+    // SPARSE: CSR over the full 2^n index space (SparseHamiltonianBase, Observables.hpp:592-699)
+    std::vector<int64_t> indptr, indices;
+    std::vector<cd> values;
     std::string name;
     std::vector<int64_t> wires;
     std::vector<double> params;
@@ -214,6 +217,35 @@ bool expand_pauli(int64_t n, const plb200_obs &o, std::vector<PauliTerm> &out, s
 
 void obs_apply(const plb200_obs &o, StateVec &s);
 
+// device copy of a CSR matrix, alive for one call
+struct DeviceCsr {
+    int64_t *indptr = nullptr, *indices = nullptr;
+    void *vals = nullptr;
+    int64_t nnz = 0;
+    DeviceCsr(const StateVec &s, const int64_t *ip, const int64_t *ix, const cd *v, int64_t nrows) {
+        PLB_CHECK(static_cast<uint64_t>(nrows) == s.length(), "sparse matrix dimension must equal the state-vector length");
+        nnz = ip[nrows];
+        s.set_device();
+        PLB_CUDA(cudaMalloc(&indptr, sizeof(int64_t) * (nrows + 1)));
+        PLB_CUDA(cudaMalloc(&indices, sizeof(int64_t) * std::max<int64_t>(nnz, 1)));
+        PLB_CUDA(cudaMalloc(&vals, sizeof(cd) * std::max<int64_t>(nnz, 1)));
+        PLB_CUDA(cudaMemcpyAsync(indptr, ip, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, s.stream));
+        PLB_CUDA(cudaMemcpyAsync(indices, ix, sizeof(int64_t) * nnz, cudaMemcpyHostToDevice, s.stream));
+        PLB_CUDA(cudaMemcpyAsync(vals, v, sizeof(cd) * nnz, cudaMemcpyHostToDevice, s.stream));
+    }
+    ~DeviceCsr() {
+        cudaFree(indptr), cudaFree(indices), cudaFree(vals);
+    }
+    DeviceCsr(const DeviceCsr &) = delete;
+    DeviceCsr &operator=(const DeviceCsr &) = delete;
+};
+// dst = A src
+void sparse_apply_to(const plb200_obs &o, StateVec &dst, const StateVec &src) {
+    DeviceCsr d(src, o.indptr.data(), o.indices.data(), o.values.data(), static_cast<int64_t>(o.indptr.size()) - 1);
+    csr_apply(dst, src, d.indptr, d.indices, d.vals, d.nnz);
+    dst.sync(); // the device copy of the matrix dies with this scope
+}
+
 void hamiltonian_apply_generic(const plb200_obs &o, StateVec &s) {
     // sum_k c_k O_k |s>  (ObservablesLQubit.hpp:156-199): accumulator + one scratch copy
     TempState orig(s, true), tmp(s, false);
@@ -241,6 +273,12 @@ void obs_apply(const plb200_obs &o, StateVec &s) {
     case plb200_obs::TENSOR:
         for (const auto &t : o.terms) obs_apply(*t, s);
         break;
+    case plb200_obs::SPARSE: {
+        TempState in(s, true);
+        sparse_apply_to(o, s, in.s);
+        s.launches += in.s.launches;
+        break;
+    }
     case plb200_obs::HAMILTONIAN: {
         std::vector<PauliTerm> terms;
         if (expand_pauli(s.n, o, terms, 1 << 16)) {
@@ -259,6 +297,10 @@ void obs_apply(const plb200_obs &o, StateVec &s) {
 
 // out-of-place: dst = O src, without touching src
 void obs_apply_to(const plb200_obs &o, StateVec &dst, const StateVec &src) {
+    if (o.kind == plb200_obs::SPARSE) {
+        sparse_apply_to(o, dst, src);
+        return;
+    }
     std::vector<PauliTerm> terms;
     if (expand_pauli(src.n, o, terms, 1 << 16) && terms.size() > 1) {
         std::vector<PauliWordMask> w(terms.size());
@@ -978,6 +1020,185 @@ int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, i
     int64_t total = lambda.s.launches + (mu ? mu->s.launches : 0);
     for (auto &h : hl) total += h->s.launches;
     const_cast<StateVec &>(ref).launches += total;
+    ABI_CATCH
+}
+
+// ------------------------------------------------------------------ sparse observables / CSR overloads
+int plb200_obs_sparse(plb200_obs **out, const int64_t *indptr, const int64_t *indices, const double *data, int64_t n_rows) {
+    ABI_TRY
+    PLB_CHECK(n_rows >= 1 && (n_rows & (n_rows - 1)) == 0, "sparse matrix dimension must be a power of two");
+    auto o = std::make_unique<plb200_obs>();
+    o->kind = plb200_obs::SPARSE;
+    o->indptr.assign(indptr, indptr + n_rows + 1);
+    const int64_t nnz = indptr[n_rows];
+    PLB_CHECK(indptr[0] == 0 && nnz >= 0, "invalid CSR row pointer");
+    o->indices.assign(indices, indices + nnz);
+    for (int64_t k = 0; k < nnz; k++) PLB_CHECK(indices[k] >= 0 && indices[k] < n_rows, "invalid CSR column index");
+    o->values = vc(data, nnz);
+    *out = o.release();
+    ABI_CATCH
+}
+// <psi| A |psi> and its variance for a CSR matrix given directly (Measurements::expval / var CSR overloads,
+// lightning_gpu/bindings/LGPUBindings.hpp:65-150, MeasurementsGPU.hpp sparse paths)
+int plb200_expval_sparse(plb200_sv *sv, const int64_t *indptr, const int64_t *indices, const double *data, int64_t n_rows,
+                         double *out) {
+    ABI_TRY
+    StateVec &s = sv->s;
+    const auto vals = vc(data, indptr[n_rows]);
+    DeviceCsr d(s, indptr, indices, vals.data(), n_rows);
+    TempState t(s, false);
+    csr_apply(t.s, s, d.indptr, d.indices, d.vals, d.nnz);
+    double r[2];
+    dot(s, t.s, s, r);
+    s.launches += t.s.launches;
+    *out = r[0];
+    ABI_CATCH
+}
+int plb200_var_sparse(plb200_sv *sv, const int64_t *indptr, const int64_t *indices, const double *data, int64_t n_rows,
+                      double *out) {
+    ABI_TRY
+    StateVec &s = sv->s;
+    const auto vals = vc(data, indptr[n_rows]);
+    DeviceCsr d(s, indptr, indices, vals.data(), n_rows);
+    TempState t(s, false);
+    csr_apply(t.s, s, d.indptr, d.indices, d.vals, d.nnz);
+    const double ms = norm2(t.s);
+    double r[2];
+    dot(s, t.s, s, r);
+    s.launches += t.s.launches;
+    *out = ms - r[0] * r[0];
+    ABI_CATCH
+}
+
+// ------------------------------------------------------------------ Hermitian eigen-decomposition (host)
+// Replaces the LAPACK zheev/cheev call the reference dlopens from scipy-openblas for Hermitian observables
+// measured with shots (core/utils/UtilLinearAlg.hpp:59-117, Observables.hpp:236-262): cyclic complex Jacobi.
+// eigvals ascending; unitary (row-major) = V^dagger, i.e. row j = conj(eigenvector j), the matrix that rotates
+// the state into the observable's eigenbasis.
+int plb200_hermitian_eigh(const double *matrix, int64_t dim, double *eigvals, double *unitary) {
+    ABI_TRY
+    PLB_CHECK(dim >= 1 && dim <= 4096, "Hermitian eigen-decomposition: dimension out of range");
+    const size_t n = static_cast<size_t>(dim);
+    std::vector<cd> A = vc(matrix, dim * dim), V(n * n, cd(0.0));
+    double scale = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        V[i * n + i] = 1.0;
+        for (size_t j = 0; j < n; j++) {
+            PLB_CHECK(std::abs(A[i * n + j] - std::conj(A[j * n + i])) <= 1e-10 * (1.0 + std::abs(A[i * n + j])),
+                      "The matrix passed to HermitianObs is not a Hermitian matrix.");
+            scale = std::max(scale, std::abs(A[i * n + j]));
+        }
+    }
+    const double tiny = std::max(scale, 1e-300) * 1e-17;
+    for (int sweep = 0; sweep < 80; sweep++) {
+        double off = 0.0;
+        for (size_t p = 0; p < n; p++)
+            for (size_t q = p + 1; q < n; q++) off = std::max(off, std::abs(A[p * n + q]));
+        if (off <= tiny) break;
+        for (size_t p = 0; p < n; p++)
+            for (size_t q = p + 1; q < n; q++) {
+                const cd apq = A[p * n + q];
+                const double mag = std::abs(apq);
+                if (mag <= tiny) continue;
+                const cd ph = apq / mag; // a_pq = |a_pq| ph
+                const double tau = (A[q * n + q].real() - A[p * n + p].real()) / (2.0 * mag);
+                const double t = (tau >= 0 ? 1.0 : -1.0) / (std::abs(tau) + std::sqrt(1.0 + tau * tau));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), sn = t * c;
+                // J = D R: D = diag(1, conj(ph)) on (p, q) makes the pivot real, R = [[c, sn], [-sn, c]]
+                const cd jpp = c, jpq = sn, jqp = -sn * std::conj(ph), jqq = c * std::conj(ph);
+                for (size_t k = 0; k < n; k++) { // A <- A J (columns p, q)
+                    const cd akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = akp * jpp + akq * jqp;
+                    A[k * n + q] = akp * jpq + akq * jqq;
+                    const cd vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = vkp * jpp + vkq * jqp;
+                    V[k * n + q] = vkp * jpq + vkq * jqq;
+                }
+                for (size_t k = 0; k < n; k++) { // A <- J^dagger A (rows p, q)
+                    const cd apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = std::conj(jpp) * apk + std::conj(jqp) * aqk;
+                    A[q * n + k] = std::conj(jpq) * apk + std::conj(jqq) * aqk;
+                }
+            }
+    }
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), size_t{0});
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return A[a * n + a].real() < A[b * n + b].real(); });
+    for (size_t j = 0; j < n; j++) {
+        eigvals[j] = A[order[j] * n + order[j]].real();
+        for (size_t k = 0; k < n; k++) {
+            const cd v = std::conj(V[k * n + order[j]]); // row j of V^dagger
+            unitary[2 * (j * n + k)] = v.real();
+            unitary[2 * (j * n + k) + 1] = v.imag();
+        }
+    }
+    ABI_CATCH
+}
+
+// ------------------------------------------------------------------ vector-Jacobian product (state cotangent)
+// VectorJacobianProduct::operator() (lightning_qubit/algorithms/VectorJacobianProduct.hpp:43-163, bound at
+// LQubitBindings.hpp:413-462): vjp[k] = i * sf_k * <G_k mu | lambda> with lambda = (U) psi and mu = dy swept
+// backwards together.  dy: 2^n host complex (re, im) pairs; out: n_tp complex pairs.
+int plb200_vjp(const plb200_sv *sv, const double *dy, const plb200_ops_t *ops, const int64_t *trainable, int64_t n_tp,
+               int apply_ops, double *out) {
+    ABI_TRY
+    const StateVec &ref = sv->s;
+    for (int64_t i = 0; i < 2 * n_tp; i++) out[i] = 0.0;
+    if (n_tp == 0) return 0;
+    const int64_t n_ops = ops->n_ops;
+    std::vector<GateCall> calls(n_ops);
+    int64_t num_param_ops = 0;
+    for (int64_t i = 0; i < n_ops; i++) {
+        calls[i] = call_from_blob(*ops, i);
+        if (!calls[i].params.empty()) num_param_ops++;
+    }
+    std::vector<int64_t> tp(trainable, trainable + n_tp);
+    TempState lambda(ref, true), mu(ref, false), mu_d(ref, false);
+    if (apply_ops)
+        for (const auto &c : calls) apply_call(lambda.s, c);
+    {
+        const size_t len = ref.length();
+        if (ref.precision == 64)
+            PLB_CUDA(cudaMemcpyAsync(mu.s.data, dy, len * 16, cudaMemcpyHostToDevice, mu.s.stream));
+        else {
+            std::vector<float> f(2 * len);
+            for (size_t i = 0; i < 2 * len; i++) f[i] = static_cast<float>(dy[i]);
+            PLB_CUDA(cudaMemcpyAsync(mu.s.data, f.data(), len * 8, cudaMemcpyHostToDevice, mu.s.stream));
+            PLB_CUDA(cudaStreamSynchronize(mu.s.stream));
+        }
+    }
+    int64_t tp_idx = n_tp - 1, current_param_idx = num_param_ops - 1;
+    for (int64_t op_idx = n_ops - 1; op_idx >= 0; op_idx--) {
+        const GateCall &c = calls[op_idx];
+        PLB_CHECK(c.params.size() <= 1, "The operation is not supported using the adjoint differentiation method");
+        if (c.name == "StatePrep" || c.name == "BasisState") continue;
+        if (tp_idx < 0) break;
+        if (!c.params.empty()) {
+            if (current_param_idx == tp[tp_idx]) {
+                copy_state(mu_d.s, mu.s);
+                GateCall gc = c;
+                gc.params.clear();
+                double gscale = 0;
+                launch_ops(mu_d.s, lower_generator(ref.n, gc, &gscale));
+                const double sf = gscale * (c.inverse ? -1.0 : 1.0);
+                double r[2];
+                dot(mu_d.s, lambda.s, mu_d.s, r); // <mu_d | lambda>
+                // i * sf * (re + i im) = sf * (-im + i re)
+                out[2 * tp_idx] = -sf * r[1];
+                out[2 * tp_idx + 1] = sf * r[0];
+                tp_idx--;
+            }
+            current_param_idx--;
+        }
+        if (tp_idx < 0) break;
+        GateCall inv = c;
+        inv.inverse = !c.inverse;
+        const auto lowered = lower_gate(ref.n, inv);
+        launch_ops(lambda.s, lowered);
+        launch_ops(mu.s, lowered);
+    }
+    lambda.s.sync();
+    const_cast<StateVec &>(ref).launches += lambda.s.launches + mu.s.launches + mu_d.s.launches;
     ABI_CATCH
 }
 

@@ -820,6 +820,22 @@ std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
     return items;
 }
 
+// A pass without ops over the lowest M index bits (one round, register bits = the highest tile bits).
+template <typename T2, class Cfg> void identity_pass(int n, int sm_count, PassParams<T2> &pp, Step &st) {
+    constexpr int M = Cfg::M, R = Cfg::R, NTB = M - R;
+    std::memset(static_cast<void *>(&pp), 0, sizeof(PassParams<T2>));
+    pp.hdr.nrounds = 1;
+    pp.hdr.ntiles = uint64_t{1} << (n - M);
+    pp.hdr.tile_ins.n = M;
+    for (int b = 0; b < M; b++) pp.hdr.tile_ins.lowmask[b] = (uint64_t{1} << b) - 1;
+    RoundHdr &rh = pp.rounds[0];
+    for (int i = 0; i < NTB; i++) rh.w[i] = swz<T2>(1u << i) * static_cast<uint32_t>(sizeof(T2));
+    for (int u = 0; u < (1 << R); u++) rh.sroff[u] = swz<T2>(static_cast<uint32_t>(u) << NTB) * static_cast<uint32_t>(sizeof(T2));
+    st = Step{};
+    st.grid = static_cast<unsigned>(std::min<uint64_t>(pp.hdr.ntiles, uint64_t(sm_count) * 3 * 64));
+    st.nrounds = 1;
+}
+
 // Route description of the caller (engine.cu / the sharded driver): swap k local index bits `lbits` against k
 // global (rank) bits while the LAST pass of the tape stores its tile.
 template <typename T2> jit::Route tile_route(const RouteSpec &rs, const PassParams<T2> &pp, jit::RouteParams<T2> &rp) {
@@ -943,14 +959,16 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
             held_st = st, have = true;
         }
     });
-    if (!have) return false;
+    if (!have) {
+        // the schedule did not end with a tile pass (stand-alone kernels at the end, or a tiny batch): an op-less
+        // pass carries the state through the route, so that EVERY rank always routes (the ranks' batches
+        // differ — controls on global bits — and they must not disagree on how the exchange happens)
+        identity_pass<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, *held, held_st);
+    }
     jit::RouteParams<T2> rp;
     const jit::Route route = tile_route<T2>(rs, *held, rp);
     jit::Kernel k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*held, route), sv.device, smem, /*force_sync=*/true);
-    if (!k) {
-        launch_plain(held_st, *held);
-        return false;
-    }
+    if (!k) fail("routed pass: the specialised kernel could not be built (NVRTC)");
     jit::launch(k, held_st.grid, nt, smem, sv.stream, sv.data, held.get(), &rp);
     sv.launches++;
     return true;
@@ -1079,7 +1097,8 @@ void run_fused(StateVec &sv, const std::vector<COp> &ops) {
 
 bool run_fused_routed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec &rs) {
     sv.set_device();
-    if (sv.n < (sv.precision == 64 ? FwdCfg<double2>::M : FwdCfg<float2>::M) + 1 || ops.size() < 2 || !jit::available(nullptr)) {
+    // depends only on the state size and on whether NVRTC exists: the same answer on every rank
+    if (sv.n < (sv.precision == 64 ? FwdCfg<double2>::M : FwdCfg<float2>::M) + 1 || !jit::available(nullptr)) {
         run_fused(sv, ops);
         return false;
     }
@@ -1160,11 +1179,11 @@ int emulate_routed_typed(int n, const std::vector<AdjItem> &items, bool scaled, 
         }
     });
     if (rc) return -1;
-    if (!have) return 0;
+    if (!have) identity_pass<T2, Cfg>(n, 148, *held, held_st);
     jit::RouteParams<T2> rp;
     const jit::Route route = tile_route<T2>(rs, *held, rp);
     if (emulate_pass_jit<T2, Cfg>(sv0, *held, route, &rp)) return 1;
-    plain(held_st, *held);
+    fail("routed pass: no specialised source");
     return 0;
 }
 int emulate_routed(int n, int precision, const std::vector<AdjItem> &items, bool scaled, void *sv0, const RouteSpec &rs,

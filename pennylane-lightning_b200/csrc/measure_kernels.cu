@@ -426,6 +426,34 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// y = A x for a CSR matrix over the full index space (SparseHamiltonian; replaces the cuSPARSE SpMV of
+// lightning_gpu/utils/LinearAlg.hpp:378-620 and LQ's apply_Sparse_Matrix).  One sub-warp of G lanes per row:
+// the lanes stride over the row's entries (x gathered through L2), partial sums meet in a shuffle reduction.
+template <typename T2, int G>
+__global__ void __launch_bounds__(kThreads)
+    csr_apply_kernel(T2 *__restrict__ y, const T2 *__restrict__ x, const int64_t *__restrict__ indptr,
+                     const int64_t *__restrict__ indices, const double2 *__restrict__ vals, uint64_t nrows) {
+    const uint64_t gtid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t row = gtid / G;
+    const int lane = static_cast<int>(gtid % G);
+    double re = 0.0, im = 0.0;
+    if (row < nrows) {
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        for (int64_t k = b + lane; k < e; k += G) {
+            const double2 a = vals[k];
+            const T2 v = x[indices[k]];
+            re += a.x * static_cast<double>(v.x) - a.y * static_cast<double>(v.y);
+            im += a.x * static_cast<double>(v.y) + a.y * static_cast<double>(v.x);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (row < nrows && lane == 0) y[row] = mk<T2>(re, im);
+}
+
 BitInsert single_insert(int bit) {
     BitInsert bi;
     bi.n = 1;
@@ -845,6 +873,30 @@ void swap_bits_peer(StateVec &sv, const int *bits, int k, int my_value, void *co
     DISPATCH(sv, (swap_multi_peer_kernel<T2><<<grid, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), a)),
              (swap_multi_peer_kernel<T2><<<grid, kThreads, 0, sv.stream>>>(static_cast<T2 *>(sv.data), a)));
     sv.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void csr_apply(StateVec &out, const StateVec &in, const int64_t *d_indptr, const int64_t *d_indices, const void *d_vals,
+               int64_t nnz) {
+    out.set_device();
+    const uint64_t nrows = out.length();
+    const double avg = static_cast<double>(nnz) / static_cast<double>(nrows);
+    const double2 *vals = static_cast<const double2 *>(d_vals);
+#define PLB_CSR(G)                                                                                       \
+    do {                                                                                                 \
+        const uint64_t nb = (nrows * (G) + kThreads - 1) / kThreads;                                     \
+        DISPATCH(out,                                                                                    \
+                 (csr_apply_kernel<T2, G><<<static_cast<unsigned>(nb), kThreads, 0, out.stream>>>(       \
+                     static_cast<T2 *>(out.data), static_cast<const T2 *>(in.data), d_indptr, d_indices, vals, nrows)), \
+                 (csr_apply_kernel<T2, G><<<static_cast<unsigned>(nb), kThreads, 0, out.stream>>>(       \
+                     static_cast<T2 *>(out.data), static_cast<const T2 *>(in.data), d_indptr, d_indices, vals, nrows))); \
+    } while (0)
+    if (avg <= 2.0) PLB_CSR(1);
+    else if (avg <= 8.0) PLB_CSR(4);
+    else if (avg <= 64.0) PLB_CSR(8);
+    else PLB_CSR(32);
+#undef PLB_CSR
+    out.launches++;
     PLB_CUDA(cudaGetLastError());
 }
 

@@ -312,6 +312,12 @@ class DistStateVector:
         if self.rank == 0:
             self.engine.set_amp(0, 1.0)
 
+    def relabel(self):
+        """Forget the wire permutation WITHOUT moving amplitudes: the slabs are reinterpreted with wire w on
+        physical bit n-1-w again (a different, equally valid state).  Benchmarks use it so that every timed
+        step schedules the same tape from the same wire map (as a run from reset() does)."""
+        self.phys = [self.n - 1 - w for w in range(self.n)]
+
     def _is_global(self, w):
         return self.phys[w] >= self.nloc
 
@@ -458,7 +464,7 @@ class DistStateVector:
                     batch.append(dict(name="Matrix", wires=w, params=[], inverse=False, ctrl_wires=cw, ctrl_values=cv,
                                       matrix=m))
             pairs = self._choose_pairs(need, rest) if rest else []
-            if pairs and fuse and getattr(self, "fused_swap", False) and len(pairs) <= 3 and len(batch) >= 2:
+            if pairs and fuse and getattr(self, "fused_swap", False) and len(pairs) <= 3:
                 self._apply_and_swap_fused(batch, pairs)
             else:
                 self.engine.apply_ops(batch, fuse=fuse)

@@ -145,4 +145,32 @@ template <class StateVectorT> class AdjointJacobian {
     }
 };
 
+// VectorJacobianProduct (lightning_qubit/algorithms/VectorJacobianProduct.hpp:43-163; bound as
+// VectorJacobianProductC64/128, LQubitBindings.hpp:413-462): vjp[k] = sum_i conj(dy_i) d psi_i / d theta_k.
+template <class StateVectorT> class VectorJacobianProduct {
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    using ComplexT = typename StateVectorT::ComplexT;
+
+  public:
+    VectorJacobianProduct() = default;
+    void operator()(std::span<ComplexT> jac, const JacobianData<StateVectorT> &jd, std::span<const ComplexT> dy,
+                    const StateVectorT &ref_data, bool apply_operations = false) {
+        PLB200_ABORT_IF_NOT(dy.size() == jd.getSizeStateVec(), "dy must have the size of the state vector");
+        if (!jd.hasTrainableParams()) return;
+        const auto &tp = jd.getTrainableParams();
+        PLB200_ABORT_IF_NOT(jac.size() == tp.size(),
+                            "The size of preallocated jacobian must be same as the number of trainable parameters.");
+        detail::OpsBlob blob;
+        jd.getOperations().fill(blob);
+        const auto v = blob.view();
+        const auto d = detail::to_c128(dy.data(), dy.size());
+        const auto t = detail::to_i64(tp);
+        std::vector<double> out(2 * jac.size());
+        PLB200_ABI(plb200_vjp(ref_data.handle(), d.data(), &v, t.data(), static_cast<int64_t>(t.size()), apply_operations,
+                              out.data()));
+        for (std::size_t i = 0; i < jac.size(); i++)
+            jac[i] = ComplexT{static_cast<PrecisionT>(out[2 * i]), static_cast<PrecisionT>(out[2 * i + 1])};
+    }
+};
+
 } // namespace Pennylane::LightningB200::Algorithms

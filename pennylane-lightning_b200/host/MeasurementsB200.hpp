@@ -94,6 +94,22 @@ template <class StateVectorT> class Measurements {
                                              static_cast<int64_t>(words.size()), &r));
         return static_cast<PrecisionT>(r);
     }
+    // CSR overloads (lightning_gpu/bindings/LGPUBindings.hpp:65-150): <psi|A|psi> and its variance for a sparse
+    // matrix over the full index space, through the engine's own CSR kernel
+    auto expval(const int64_t *indptr, std::size_t indptr_size, const int64_t *indices, const ComplexT *data,
+                std::size_t nnz) -> PrecisionT {
+        const auto d = detail::to_c128(data, nnz);
+        double r = 0;
+        PLB200_ABI(plb200_expval_sparse(sv_.handle(), indptr, indices, d.data(), static_cast<int64_t>(indptr_size) - 1, &r));
+        return static_cast<PrecisionT>(r);
+    }
+    auto var(const int64_t *indptr, std::size_t indptr_size, const int64_t *indices, const ComplexT *data,
+             std::size_t nnz) -> PrecisionT {
+        const auto d = detail::to_c128(data, nnz);
+        double r = 0;
+        PLB200_ABI(plb200_var_sparse(sv_.handle(), indptr, indices, d.data(), static_cast<int64_t>(indptr_size) - 1, &r));
+        return static_cast<PrecisionT>(r);
+    }
     auto generate_samples(std::size_t num_samples) -> std::vector<std::size_t> {
         std::vector<uint64_t> out(num_samples * sv_.getNumQubits());
         PLB200_ABI(plb200_generate_samples(sv_.handle(), nullptr, -1, static_cast<int64_t>(num_samples), seed_arg(),

@@ -107,11 +107,24 @@ template <class StateVectorT> class HermitianObs final : public Observable<State
     }
     [[nodiscard]] auto getMatrix() const -> const MatrixT & { return matrix_; }
     [[nodiscard]] auto getObsName() const -> std::string override { return "Hermitian"; }
-    void applyInPlaceShots(StateVectorT &, std::vector<std::vector<PrecisionT>> &,
-                           std::vector<std::size_t> &) const override {
-        // the reference diagonalises with LAPACK zheev loaded at run time from scipy-openblas
-        // (Observables.hpp:236-262); SURVEY.md section 8(f) lists this as next-tier.
-        PLB200_ABORT("Hermitian observables do not support shot measurement in the B200 backend yet.");
+    // Rotate into the observable's eigenbasis (Observables.hpp:236-303): the reference diagonalises with LAPACK
+    // zheev loaded at run time from scipy-openblas; here the engine's own Jacobi solver (plb200_hermitian_eigh).
+    void applyInPlaceShots(StateVectorT &sv, std::vector<std::vector<PrecisionT>> &eigenValues,
+                           std::vector<std::size_t> &ob_wires) const override {
+        if (eigenVals_.empty()) {
+            const std::size_t dim = std::size_t{1} << wires_.size();
+            const auto m = detail::to_c128(matrix_.data(), matrix_.size());
+            std::vector<double> ev(dim), u(2 * dim * dim);
+            PLB200_ABI(plb200_hermitian_eigh(m.data(), static_cast<int64_t>(dim), ev.data(), u.data()));
+            eigenVals_.assign(ev.begin(), ev.end());
+            unitary_.resize(dim * dim);
+            for (std::size_t i = 0; i < dim * dim; i++)
+                unitary_[i] = ComplexT{static_cast<PrecisionT>(u[2 * i]), static_cast<PrecisionT>(u[2 * i + 1])};
+        }
+        eigenValues.clear();
+        ob_wires = wires_;
+        sv.applyMatrix(unitary_, wires_);
+        eigenValues.push_back(eigenVals_);
     }
     [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
 
@@ -121,6 +134,57 @@ template <class StateVectorT> class HermitianObs final : public Observable<State
         return matrix_ == o.matrix_ && wires_ == o.wires_;
     }
     MatrixT matrix_;
+    std::vector<std::size_t> wires_;
+    mutable std::vector<PrecisionT> eigenVals_;
+    mutable MatrixT unitary_;
+};
+
+// SparseHamiltonian (Observables.hpp:592-699, lightning_gpu/observables/ObservablesGPU.hpp): CSR over the full
+// index space, applied by the engine's CSR kernel.
+template <class StateVectorT> class SparseHamiltonian final : public Observable<StateVectorT> {
+  public:
+    using PrecisionT = typename StateVectorT::PrecisionT;
+    using ComplexT = typename StateVectorT::ComplexT;
+    using IdxT = int64_t;
+    SparseHamiltonian(std::vector<ComplexT> data, std::vector<IdxT> indices, std::vector<IdxT> offsets,
+                      std::vector<std::size_t> wires)
+        : data_{std::move(data)}, indices_{std::move(indices)}, offsets_{std::move(offsets)}, wires_{std::move(wires)} {
+        PLB200_ABORT_IF(data_.size() != indices_.size(), "data and indices must have the same size");
+        PLB200_ABORT_IF(offsets_.empty(), "offsets must not be empty");
+        const auto d = detail::to_c128(data_.data(), data_.size());
+        PLB200_ABI(plb200_obs_sparse(&this->h_, offsets_.data(), indices_.data(), d.data(),
+                                     static_cast<int64_t>(offsets_.size()) - 1));
+    }
+    static auto create(std::initializer_list<ComplexT> data, std::initializer_list<IdxT> indices,
+                       std::initializer_list<IdxT> offsets, std::initializer_list<std::size_t> wires)
+        -> std::shared_ptr<SparseHamiltonian> {
+        return std::make_shared<SparseHamiltonian>(std::vector<ComplexT>(data), std::vector<IdxT>(indices),
+                                                   std::vector<IdxT>(offsets), std::vector<std::size_t>(wires));
+    }
+    void applyInPlaceShots(StateVectorT &, std::vector<std::vector<PrecisionT>> &,
+                           std::vector<std::size_t> &) const override {
+        PLB200_ABORT("SparseHamiltonian observables do not support shot measurement.");
+    }
+    [[nodiscard]] auto getObsName() const -> std::string override {
+        std::ostringstream s;
+        s << "SparseHamiltonian: {\n'data' : \n";
+        for (const auto &d : data_) s << "{" << d.real() << ", " << d.imag() << "}, ";
+        s << "\n'indices' : \n";
+        for (const auto &i : indices_) s << i << ", ";
+        s << "\n'offsets' : \n";
+        for (const auto &o : offsets_) s << o << ", ";
+        s << "\n}";
+        return s.str();
+    }
+    [[nodiscard]] auto getWires() const -> std::vector<std::size_t> override { return wires_; }
+
+  private:
+    [[nodiscard]] bool isEqual(const Observable<StateVectorT> &other) const override {
+        const auto &o = static_cast<const SparseHamiltonian &>(other);
+        return data_ == o.data_ && indices_ == o.indices_ && offsets_ == o.offsets_;
+    }
+    std::vector<ComplexT> data_;
+    std::vector<IdxT> indices_, offsets_;
     std::vector<std::size_t> wires_;
 };
 

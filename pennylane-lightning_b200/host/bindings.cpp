@@ -189,6 +189,21 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
             return py::isinstance<Hamiltonian<SV>>(other) && a == other.cast<const Hamiltonian<SV> &>();
         });
 
+    using SpH = SparseHamiltonian<SV>;
+    using idx_arr = py::array_t<int64_t, py::array::c_style | py::array::forcecast>;
+    py::class_<SpH, std::shared_ptr<SpH>, ObsT>(obs, ("SparseHamiltonianC" + bits).c_str(), py::module_local())
+        .def(py::init([](const np_arr_c<PrecisionT> &data, const idx_arr &indices, const idx_arr &offsets,
+                         const std::vector<std::size_t> &wires) {
+            return std::make_shared<SpH>(std::vector<ComplexT>(data.data(), data.data() + data.size()),
+                                         std::vector<int64_t>(indices.data(), indices.data() + indices.size()),
+                                         std::vector<int64_t>(offsets.data(), offsets.data() + offsets.size()), wires);
+        }))
+        .def("__repr__", &SpH::getObsName)
+        .def("get_wires", &SpH::getWires)
+        .def("__eq__", [](const SpH &a, py::handle other) {
+            return py::isinstance<SpH>(other) && a == other.cast<const SpH &>();
+        });
+
     // ------------------------------------------------------------------ MeasurementsC{64,128}
     using M = Measurements<SV>;
     py::class_<M>(m, ("MeasurementsC" + bits).c_str())
@@ -215,6 +230,14 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
             return mm.expval(words, wires, std::vector<PrecisionT>(coeffs.data(), coeffs.data() + coeffs.size()));
         })
         // shot-based C++ API of MeasurementsBase (not bound by the reference; exposed for the parity tests)
+        .def("expval", [](M &mm, const idx_arr &indptr, const idx_arr &indices, const np_arr_c<PrecisionT> &data) {
+            return mm.expval(indptr.data(), static_cast<std::size_t>(indptr.size()), indices.data(), data.data(),
+                             static_cast<std::size_t>(data.size()));
+        }, "Expected value of a sparse Hamiltonian (CSR).")
+        .def("var", [](M &mm, const idx_arr &indptr, const idx_arr &indices, const np_arr_c<PrecisionT> &data) {
+            return mm.var(indptr.data(), static_cast<std::size_t>(indptr.size()), indices.data(), data.data(),
+                          static_cast<std::size_t>(data.size()));
+        }, "Variance of a sparse Hamiltonian (CSR).")
         .def("expval_shots", [](M &mm, const ObsPtr &o, std::size_t shots, const std::vector<std::size_t> &range) {
             return mm.expval(*o, shots, range);
         }, py::arg("obs"), py::arg("num_shots"), py::arg("shot_range") = std::vector<std::size_t>{})
@@ -273,6 +296,17 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
         adj.adjointJacobian(std::span<PrecisionT>{jac}, jd, svec, false);
         return py::array_t<PrecisionT>(py::cast(jac));
     };
+    using Vjp = VectorJacobianProduct<SV>;
+    py::class_<Vjp>(alg, ("VectorJacobianProductC" + bits).c_str(), py::module_local())
+        .def(py::init<>())
+        .def("__call__", [](Vjp &v, const SV &svec, const Ops &operations, const np_arr_c<PrecisionT> &dy,
+                            const std::vector<std::size_t> &trainableParams) {
+            std::vector<ComplexT> out(trainableParams.size(), ComplexT{});
+            const JacobianData<SV> jd{operations.getTotalNumParams(), svec.getLength(), svec.getData(), {}, operations,
+                                      trainableParams};
+            v(std::span<ComplexT>{out}, jd, std::span<const ComplexT>{dy.data(), static_cast<std::size_t>(dy.size())}, svec);
+            return py::array_t<ComplexT>(py::cast(out));
+        }, "Vector Jacobian Product method.");
     py::class_<Adj>(alg, ("AdjointJacobianC" + bits).c_str(), py::module_local())
         .def(py::init<>())
         .def("__call__", call_adj, "Adjoint Jacobian method.")

@@ -27,18 +27,32 @@ def emu():
     return lib
 
 
-@pytest.mark.parametrize("dtype,g,nloc,lbits", [
-    (np.complex128, 1, 13, [9]),            # one bit, inside or outside the tile depending on the schedule
-    (np.complex128, 2, 13, [12, 5]),        # two bits
-    (np.complex128, 3, 13, [11, 7, 4]),     # three bits: 8-way all-to-all
-    (np.complex64, 2, 15, [14, 6]),
+def _tape(kind, nloc):
+    if kind == "random":
+        return circuits.random_circuit(nloc, 3, 77)
+    if kind == "tail":  # ends with gates the scheduler runs stand-alone: an op-less pass carries the route
+        return circuits.random_circuit(nloc, 2, 78) + [circuits.op("IsingXX", [1, 4], [0.3]),
+                                                       circuits.op("DoubleExcitation", [0, 2, 5, 7], [0.9])]
+    if kind == "one":  # a single gate: nothing to fuse
+        return [circuits.op("RX", [3], [0.4])]
+    return []  # "empty": a pure exchange
+
+
+@pytest.mark.parametrize("dtype,g,nloc,lbits,kind", [
+    (np.complex128, 1, 13, [9], "random"),           # one bit, inside or outside the tile depending on the schedule
+    (np.complex128, 2, 13, [12, 5], "random"),       # two bits
+    (np.complex128, 3, 13, [11, 7, 4], "random"),    # three bits: 8-way all-to-all
+    (np.complex64, 2, 15, [14, 6], "random"),
+    (np.complex128, 2, 13, [10, 3], "tail"),
+    (np.complex128, 1, 13, [6], "one"),
+    (np.complex128, 2, 13, [12, 8], "empty"),
 ])
-def test_routed_pass_equals_apply_then_swap(emu, plb, dtype, g, nloc, lbits, monkeypatch):
+def test_routed_pass_equals_apply_then_swap(emu, plb, dtype, g, nloc, lbits, kind, monkeypatch):
     monkeypatch.setenv("PLB200_EMU_JIT", "1")
     world, n = 1 << g, nloc + g
     k = len(lbits)
     # the swapped global bits: rank bits 0..k-1  <->  local bits lbits[i]
-    ops = circuits.random_circuit(nloc, 3, 77)  # the same local tape on every rank (targets all local)
+    ops = _tape(kind, nloc)  # the same local tape on every rank (targets all local)
     full = random_state(n, dtype, 5)
     slabs = [full[r << nloc:(r + 1) << nloc].copy() for r in range(world)]  # the tape runs in place on these
     alts = [np.zeros(1 << nloc, dtype=dtype) for _ in range(world)]
@@ -57,9 +71,7 @@ def test_routed_pass_equals_apply_then_swap(emu, plb, dtype, g, nloc, lbits, mon
                                             dst, C.byref(routed))
         assert rc == 0, emu.plb200_emu_last_error()
         n_routed += routed.value
-    assert n_routed in (0, world)  # the schedule (hence routability) is the same on every rank
-    if n_routed == 0:
-        pytest.skip("the last round of this schedule is not line-coalesced: the engine would swap stand-alone")
+    assert n_routed == world  # every rank always routes (an op-less pass if its schedule has no final tile pass)
     got = np.concatenate(alts)
     # oracle: apply the local tape to every slab (= the tape on the low nloc qubits of the full state) ...
     ref = np_oracle.StateVector(n, np.complex128)
