@@ -129,6 +129,8 @@ int plb200_sv_apply_generator(plb200_sv *sv, const char *name, const int64_t *ct
 int plb200_validate_op(int64_t num_qubits, const char *name, const int64_t *ctrl_wires,
                        const uint8_t *ctrl_values, int64_t n_ctrl, const int64_t *wires, int64_t n_wires,
                        int inverse, const double *params, int64_t n_params);
+/* the same for a whole blob (ops with an explicit matrix, "PauliRot[word]" entries of the lazy queue) */
+int plb200_validate_ops(int64_t num_qubits, const plb200_ops_t *ops);
 /* applyOperations over a whole tape; `fuse` != 0 lets the engine schedule the tape into
  * cache-blocked passes (same arithmetic per gate, fewer HBM sweeps). */
 int plb200_sv_apply_ops(plb200_sv *sv, const plb200_ops_t *ops, int fuse);

@@ -96,6 +96,9 @@ struct StateVec {
 void launch_op(StateVec &sv, const COp &op);
 void launch_ops(StateVec &sv, const std::vector<COp> &ops);
 
+// dense_mma.cu: OP_DENSE on 5..7 wires through the tensor cores (DMMA / 3xTF32); false = not applicable
+bool launch_dense_mma(StateVec &sv, const COp &op);
+
 // measure_kernels.cu
 double norm2(StateVec &sv);
 void dot(const StateVec &a, const StateVec &b, StateVec &scratch_owner, double out[2]);

@@ -578,6 +578,11 @@ int plb200_validate_op(int64_t n, const char *name, const int64_t *cw, const uin
     (void)lower_gate(n, make_call(name, cw, cv, nc, w, nw, inverse, params, np));
     ABI_CATCH
 }
+int plb200_validate_ops(int64_t n, const plb200_ops_t *ops) {
+    ABI_TRY
+    for (int64_t i = 0; i < ops->n_ops; i++) (void)lower_gate(n, call_from_blob(*ops, i));
+    ABI_CATCH
+}
 int plb200_sv_apply_matrix(plb200_sv *sv, const double *matrix, const int64_t *cw, const uint8_t *cv, int64_t nc,
                            const int64_t *w, int64_t nw, int inverse) {
     ABI_TRY

@@ -321,8 +321,8 @@ template <typename T2> void launch_diag(StateVec &sv, const COp &op) {
         std::vector<T2> h(op.diag.size());
         for (size_t i = 0; i < h.size(); i++) h[i] = mk<T2>(op.diag[i].real(), op.diag[i].imag());
         T2 *t = static_cast<T2 *>(sv.table_buf(h.size() * sizeof(T2)));
+        // pageable source: the call returns once the bytes are staged (no stream sync needed for h's lifetime)
         PLB_CUDA(cudaMemcpyAsync(t, h.data(), h.size() * sizeof(T2), cudaMemcpyHostToDevice, sv.stream));
-        PLB_CUDA(cudaStreamSynchronize(sv.stream)); // h goes out of scope
         a.table = t;
         launch_diag_mode<T2, DIAG_TABLE>(sv, a, op.cmask);
     }
@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 template <typename T2> void launch_dense(StateVec &sv, const COp &op) {
+    if (op.k() >= 5 && launch_dense_mma(sv, op)) return; // batched complex GEMM on the tensor cores
     DenseArgs<T2> a;
     const int k = op.k();
     const int D = 1 << k;
@@ -408,8 +409,8 @@ template <typename T2> void launch_dense(StateVec &sv, const COp &op) {
             h[small ? static_cast<size_t>(r) * D + c : static_cast<size_t>(c) * D + r] = mk<T2>(e.real(), e.imag());
         }
     T2 *t = static_cast<T2 *>(sv.table_buf(h.size() * sizeof(T2)));
+    // pageable source: cudaMemcpyAsync returns once the bytes are staged, so `h` may die without a stream sync
     PLB_CUDA(cudaMemcpyAsync(t, h.data(), h.size() * sizeof(T2), cudaMemcpyHostToDevice, sv.stream));
-    PLB_CUDA(cudaStreamSynchronize(sv.stream));
     a.mat = t;
     T2 *d = static_cast<T2 *>(sv.data);
     if (small) {

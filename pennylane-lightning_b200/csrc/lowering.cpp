@@ -441,6 +441,12 @@ std::vector<COp> lower_matrix(int64_t n, const std::vector<cd> &matrix,
 std::vector<COp> lower_gate(int64_t n, const GateCall &g) {
     if (!g.matrix.empty() && !gate_known(g.name))
         return lower_matrix(n, g.matrix, g.wires, g.ctrl_wires, g.ctrl_values, g.inverse);
+    // "PauliRot[XYZ]": applyPauliRot travelling through a tape (the lazy gate queue of the C++ mirror)
+    if (g.name.rfind("PauliRot[", 0) == 0 && g.name.back() == ']') {
+        PLB_CHECK(g.params.size() == 1, "PauliRot needs one parameter");
+        PLB_CHECK(g.ctrl_wires.empty(), "Controlled gate operation does not exist for PauliRot");
+        return lower_pauli_rot(n, g.wires, g.inverse, g.params[0], g.name.substr(9, g.name.size() - 10));
+    }
     auto it = gate_table().find(g.name);
     PLB_CHECK(it != gate_table().end(), "Gate operation does not exist for " + g.name);
     const GateInfo gi = it->second;

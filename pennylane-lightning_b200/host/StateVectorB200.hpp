@@ -223,9 +223,25 @@ template <class Precision = double> class StateVectorB200 {
         PLB200_ABI(plb200_sv_apply_ops(h_, &v, fuse ? 1 : 0));
     }
 
+    // Matrices on up to kLazyMatrixWires wires and Pauli rotations join the lazy queue (validated now, applied
+    // with the rest of the tape as fused passes); larger matrices flush and run at once.
+    static constexpr std::size_t kLazyMatrixWires = 4;
+    bool queue_matrix(const ComplexT *matrix, const std::vector<std::size_t> &controlled_wires,
+                      const std::vector<bool> &controlled_values, const std::vector<std::size_t> &wires, bool inverse) {
+        if (!lazy_ || wires.empty() || wires.size() > kLazyMatrixWires) return false;
+        const std::vector<ComplexT> m(matrix, matrix + (std::size_t{1} << (2 * wires.size())));
+        detail::OpsBlob one;
+        one.template add<PrecisionT>("Matrix", wires, inverse, {}, controlled_wires, controlled_values, m);
+        const auto v = one.view();
+        PLB200_ABI(plb200_validate_ops(static_cast<int64_t>(num_qubits_), &v));
+        queue_.template add<PrecisionT>("Matrix", wires, inverse, {}, controlled_wires, controlled_values, m);
+        if (queue_.names.size() >= kMaxQueue) flush();
+        return true;
+    }
     void applyMatrix(const ComplexT *matrix, const std::vector<std::size_t> &wires, bool inverse = false) {
-        flush();
         PLB200_ABORT_IF(wires.empty(), "Number of wires must be larger than 0");
+        if (queue_matrix(matrix, {}, {}, wires, inverse)) return;
+        flush();
         const auto w = detail::to_i64(wires);
         const auto m = detail::to_c128(matrix, std::size_t{1} << (2 * wires.size()));
         PLB200_ABI(plb200_sv_apply_matrix(h_, m.data(), nullptr, nullptr, 0, w.data(), static_cast<int64_t>(w.size()),
@@ -239,10 +255,11 @@ template <class Precision = double> class StateVectorB200 {
     void applyControlledMatrix(const ComplexT *matrix, const std::vector<std::size_t> &controlled_wires,
                                const std::vector<bool> &controlled_values, const std::vector<std::size_t> &wires,
                                bool inverse = false) {
-        flush();
         PLB200_ABORT_IF(wires.empty(), "Number of wires must be larger than 0");
         PLB200_ABORT_IF_NOT(controlled_wires.size() == controlled_values.size(),
                             "`controlled_wires` must have the same size as `controlled_values`.");
+        if (queue_matrix(matrix, controlled_wires, controlled_values, wires, inverse)) return;
+        flush();
         const auto w = detail::to_i64(wires), cw = detail::to_i64(controlled_wires);
         const auto cv = detail::to_u8(controlled_values);
         const auto m = detail::to_c128(matrix, std::size_t{1} << (2 * wires.size()));
@@ -251,9 +268,19 @@ template <class Precision = double> class StateVectorB200 {
     }
     void applyPauliRot(const std::vector<std::size_t> &wires, bool inverse, const std::vector<PrecisionT> &params,
                        const std::string &word) {
-        flush();
         PLB200_ABORT_IF_NOT(wires.size() == word.size(), "wires and word have incompatible dimensions.");
         PLB200_ABORT_IF(params.empty(), "PauliRot needs one parameter");
+        if (lazy_) {
+            const std::string name = "PauliRot[" + word + "]";
+            detail::OpsBlob one;
+            one.template add<PrecisionT>(name, wires, inverse, {params[0]});
+            const auto v = one.view();
+            PLB200_ABI(plb200_validate_ops(static_cast<int64_t>(num_qubits_), &v));
+            queue_.template add<PrecisionT>(name, wires, inverse, {params[0]});
+            if (queue_.names.size() >= kMaxQueue) flush();
+            return;
+        }
+        flush();
         const auto w = detail::to_i64(wires);
         PLB200_ABI(plb200_sv_apply_pauli_rot(h_, w.data(), static_cast<int64_t>(w.size()), inverse,
                                              static_cast<double>(params[0]), word.c_str()));
