@@ -4,6 +4,8 @@
 // and the local half of the distributed index-bit swap.
 // All sums accumulate in fp64 per thread, reduce by warp shuffle, then by a fixed-order second
 // stage -> deterministic for a given launch shape.
+#include <type_traits>
+
 #include "device.cuh"
 
 #include <algorithm>
@@ -219,22 +221,22 @@ __global__ void __launch_bounds__(kThreads)
 // <psi| Z-word |psi> for up to W diagonal words in ONE read of the state:
 // sum_i |a_i|^2 (-1)^{popcount(i & z_q)}, q < W  (expval of PauliZ on every wire, ZZ terms of an Ising
 // Hamiltonian, ...).  partials laid out [block][W].
+template <int W> struct ZMasks {
+    uint64_t z[W];
+};
 template <typename T2, int W>
 __global__ void __launch_bounds__(kThreads)
-    zwords_kernel(const T2 *__restrict__ a, uint64_t len, const WordDev *__restrict__ words, int nw, double *partials) {
-    __shared__ uint64_t zs[W];
-    if (threadIdx.x < W) zs[threadIdx.x] = threadIdx.x < nw ? words[threadIdx.x].z : 0;
-    __syncthreads();
-    uint64_t z[W];
+    zwords_kernel(const T2 *__restrict__ a, uint64_t len, const __grid_constant__ ZMasks<W> m, double *partials) {
+    // the sign masks sit in the constant bank (uniform loads): W accumulators per thread, ONE read of the state
     double v[W];
 #pragma unroll
-    for (int q = 0; q < W; q++) z[q] = zs[q], v[q] = 0;
+    for (int q = 0; q < W; q++) v[q] = 0;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
         const T2 x = a[i];
         const double p = static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
 #pragma unroll
-        for (int q = 0; q < W; q++) v[q] += (__popcll(i & z[q]) & 1) ? -p : p;
+        for (int q = 0; q < W; q++) v[q] += (__popcll(i & m.z[q]) & 1) ? -p : p;
     }
     block_reduce_store<W>(v, partials + static_cast<size_t>(blockIdx.x) * W);
 }
@@ -609,25 +611,34 @@ void pauli_inner(StateVec &a, const StateVec &b, const PauliWordMask *words, int
     for (int64_t k = 0; k < n_words && all_diag; k++)
         all_diag = words[k].x == 0 && words[k].cmask == 0 && words[k].ny == 0;
     if (all_diag && n_words > 1) {
-        constexpr int W = 8;
+        // 8 words per read of the state, or 32 when there are many (<Z_w> on every wire of a 30-qubit register
+        // is ONE sweep instead of four)
         const int nb = reduce_blocks(a, a.length());
-        for (int64_t w0 = 0; w0 < n_words; w0 += W) {
-            const int nw = static_cast<int>(std::min<int64_t>(W, n_words - w0));
-            auto h = to_dev_words(words + w0, nw);
-            WordDev *dw = static_cast<WordDev *>(a.table_buf(h.size() * sizeof(WordDev)));
-            PLB_CUDA(cudaMemcpyAsync(dw, h.data(), h.size() * sizeof(WordDev), cudaMemcpyHostToDevice, a.stream));
-            PLB_CUDA(cudaStreamSynchronize(a.stream));
+        auto run = [&](auto wtag, int64_t w0, int nw) {
+            constexpr int W = decltype(wtag)::value;
+            ZMasks<W> m;
+            for (int q = 0; q < W; q++) m.z[q] = q < nw ? words[w0 + q].z : 0;
             double *part = a.reduce_buf(static_cast<size_t>(W) * nb + W + 8);
             DISPATCH(a,
-                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), dw,
-                                                                        nw, part)),
-                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), dw,
-                                                                        nw, part)));
+                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), m, part)),
+                     (zwords_kernel<T2, W><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), a.length(), m, part)));
             a.launches++;
             PLB_CUDA(cudaGetLastError());
             double r[W];
             finish_reduce<W>(a, part, 1, nb, r);
             for (int q = 0; q < nw; q++) out[2 * (w0 + q)] = r[q], out[2 * (w0 + q) + 1] = 0.0;
+        };
+        int64_t w0 = 0;
+        while (w0 < n_words) {
+            const int64_t left = n_words - w0;
+            if (left > 8) {
+                const int nw = static_cast<int>(std::min<int64_t>(32, left));
+                run(std::integral_constant<int, 32>{}, w0, nw);
+                w0 += nw;
+            } else {
+                run(std::integral_constant<int, 8>{}, w0, static_cast<int>(left));
+                w0 += left;
+            }
         }
         return;
     }

@@ -227,6 +227,14 @@ class LocalEngine:
         wires = [[w] for w in local_wires] + [[0]]
         return self.sv.expval_pauli_words_each(words, wires)
 
+    def pauli_sums(self, words, local_wires):
+        """un-normalised <slab| P_k |slab> for Pauli words over LOCAL wires (engine wire numbering)"""
+        return np.asarray(self.sv.expval_pauli_words_each(words, local_wires))
+
+    def probs(self, local_wires=None):
+        """un-normalised |a_i|^2 marginal over the given local wires (all local wires when None)"""
+        return self.sv.probs(local_wires)
+
     def host_state(self):
         return self.sv.get_state()
 
@@ -561,6 +569,115 @@ class DistStateVector:
     def norm2(self):
         self.expval_z_all()
         return self.last_norm2
+
+    # -- general measurements on the sharded state (local reduction -> all_reduce of fp64 vectors;
+    #    replaces MeasurementsGPUMPI.hpp / MeasurementsKokkosMPI: expval / probs / generate_samples)
+    def _make_wires_local(self, wires):
+        """Bring the given wires onto local bits (one exchange), evicting wires outside the set."""
+        need = [w for w in wires if self._is_global(w)]
+        if not need:
+            return
+        if len(set(wires)) > self.nloc:
+            raise ValueError("more wires than local qubits: cannot be made local at once")
+        cand = [w for w in range(self.n) if not self._is_global(w) and w not in wires]
+        low = 3 if self.dtype == np.complex128 else 4
+        cand.sort(key=lambda w: (self.phys[w] >= low, self.phys[w]), reverse=True)
+        pairs = list(zip(need, cand))
+        if getattr(self, "fused_swap", False) and len(pairs) <= 3 and self.nloc >= 13:
+            self._apply_and_swap_fused([], pairs)
+        else:
+            self._swap_pairs(pairs)
+
+    def expval_pauli_words(self, words, wires, coeffs=None):
+        """<P_k> for Pauli words (strings over I/X/Y/Z) on the given wires; with coeffs: sum_k c_k <P_k>.
+        X / Y letters must act on local wires (they are swapped in, word by word if needed); Z / I letters on
+        global wires become a rank-dependent sign.  One local reduction per batch of words + ONE all_reduce."""
+        out = np.zeros(len(words) + 1)
+        batch = []  # (index, local word, local wires, sign)
+
+        def flush():
+            if not batch:
+                return
+            lw = [b[1] for b in batch] + ["I"]
+            ww = [b[2] for b in batch] + [[0]]
+            sums = self.engine.pauli_sums(lw, ww)
+            for (k, _, _, sign), s_ in zip(batch, sums[:-1]):
+                out[k] += sign * s_
+            out[len(words)] = sums[-1]
+            batch.clear()
+
+        for k, (word, ws) in enumerate(zip(words, wires)):
+            xy = [w for c, w in zip(word, ws) if c in "XY"]
+            if any(self._is_global(w) for w in xy):
+                flush()  # the layout changes: evaluate what was collected under the old one first
+                self._make_wires_local(xy)
+            sign, lword, lws = 1.0, "", []
+            for c, w in zip(word, ws):
+                if self._is_global(w):
+                    if c == "Z" and self._rank_bit(w):
+                        sign = -sign
+                else:
+                    lword += c
+                    lws.append(self._lw(w))
+            if not lws:
+                free = next(w for w in range(self.n) if not self._is_global(w))
+                lword, lws = "I", [self._lw(free)]
+            batch.append((k, lword, lws, sign))
+        flush()
+        if out[len(words)] == 0.0:  # no word evaluated the norm slot (empty list)
+            out[len(words)] = self.engine.pauli_sums(["I"], [[0]])[0]
+        out = self._allreduce(out)
+        self.last_norm2 = float(out[len(words)])
+        vals = out[: len(words)]
+        return float(np.dot(coeffs, vals)) if coeffs is not None else vals
+
+    def probs(self, wires=None):
+        """Marginal probabilities over `wires` (all wires when None), ordered by the given wire order
+        (MeasurementsLQubit.hpp:90-163 semantics): local marginal over the local target wires, placed by this
+        rank's values on the global target wires, then one all_reduce of the 2^k vector."""
+        wires = list(range(self.n)) if wires is None else list(wires)
+        k = len(wires)
+        if k > 26:
+            raise ValueError("probs over more than 26 wires is not gathered")
+        loc = [w for w in wires if not self._is_global(w)]
+        p_loc = np.asarray(self.engine.probs([self._lw(w) for w in loc])) if loc else np.array(
+            [self.engine.pauli_sums(["I"], [[0]])[0]])
+        out = np.zeros(1 << k)
+        # index of a local outcome inside the full 2^k table: local wires keep their relative order
+        pos = {w: k - 1 - i for i, w in enumerate(wires)}  # wire -> bit position in the output index
+        base = 0
+        for w in wires:
+            if self._is_global(w) and self._rank_bit(w):
+                base |= 1 << pos[w]
+        idx = np.zeros(1 << len(loc), dtype=np.int64)
+        for j, w in enumerate(loc):
+            bit = (np.arange(1 << len(loc)) >> (len(loc) - 1 - j)) & 1
+            idx |= bit << pos[w]
+        np.add.at(out, idx + base, p_loc)
+        return self._allreduce(out)
+
+    def generate_samples(self, shots, seed=0):
+        """Computational-basis samples of all wires, shape (shots, n), wire 0 first.  Per-rank mass -> the same
+        multinomial split on every rank (shared seed, no communication) -> each rank draws its share from its
+        slab's distribution -> local bit strings are translated through the wire map and gathered.  (Not the
+        reference's alias-table stream: a sharded state has no single table; the distribution is the same.)"""
+        p_loc = np.asarray(self.engine.probs(None), dtype=np.float64)
+        masses = self._allreduce(np.eye(self.world)[self.rank] * p_loc.sum())
+        masses = masses / masses.sum()
+        counts = np.random.default_rng(seed).multinomial(shots, masses)
+        mine = int(counts[self.rank])
+        rng = np.random.default_rng([seed, self.rank])
+        cdf = np.cumsum(p_loc)
+        draws = np.searchsorted(cdf, rng.random(mine) * cdf[-1], side="right").clip(0, len(cdf) - 1)
+        bits = np.zeros((mine, self.n), dtype=np.uint64)
+        for w in range(self.n):
+            if self._is_global(w):
+                bits[:, w] = self._rank_bit(w)
+            else:
+                bits[:, w] = (draws >> self.phys[w]) & 1
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, bits, group=self.group)
+        return np.concatenate(parts, axis=0)
 
     def gather_state(self):
         """Full state in logical wire order on every rank (tests, small n only)."""

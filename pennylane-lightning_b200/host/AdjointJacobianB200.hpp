@@ -4,10 +4,13 @@
 #pragma once
 #include <complex>
 #include <memory>
+#include <exception>
 #include <span>
+#include <thread>
 #include <string>
 #include <vector>
 
+#include "DevTag.hpp"
 #include "ObservablesB200.hpp"
 #include "StateVectorB200.hpp"
 
@@ -137,11 +140,52 @@ template <class StateVectorT> class AdjointJacobian {
                                            static_cast<int64_t>(t.size()), apply_operations, out.data()));
         for (std::size_t i = 0; i < out.size(); i++) jac[i] = static_cast<PrecisionT>(out[i]);
     }
-    // LGPU's batched entry point distributes observables over a DevicePool; one B200 holds every
-    // H lambda_i that fits, so the batched form forwards to the single-device sweep.
+    // Observable batching over the GPUs of the box (lightning_gpu/algorithms/AdjointJacobianGPU.hpp:123-225): the
+    // observables are cut into one contiguous chunk per device, every chunk runs its own backward sweep on its own
+    // GPU from a copy of the state (one std::thread and one DevTag per device), rows land in jac in order.
     void batchAdjointJacobian(std::span<PrecisionT> jac, const JacobianData<StateVectorT> &jd,
                               const StateVectorT &ref_data, bool apply_operations = false) {
-        adjointJacobian(jac, jd, ref_data, apply_operations);
+        const auto &obs = jd.getObservables();
+        const auto &tp = jd.getTrainableParams();
+        if (!jd.hasTrainableParams()) return;
+        const std::size_t n_dev = std::min<std::size_t>(DevicePool<int>::getTotalDevices(), obs.size());
+        if (n_dev <= 1) {
+            adjointJacobian(jac, jd, ref_data, apply_operations);
+            return;
+        }
+        PLB200_ABORT_IF_NOT(jac.size() == tp.size() * obs.size(),
+                            "The size of preallocated jacobian must be same as the number of trainable parameters "
+                            "times the number of observables provided.");
+        const auto host = ref_data.getDataVector();
+        detail::OpsBlob blob;
+        jd.getOperations().fill(blob);
+        const auto v = blob.view();
+        const auto t = detail::to_i64(tp);
+        std::vector<std::thread> threads;
+        std::vector<std::exception_ptr> errors(n_dev);
+        const std::size_t per = (obs.size() + n_dev - 1) / n_dev;
+        for (std::size_t d = 0; d < n_dev; d++) {
+            const std::size_t first = d * per, last = std::min(obs.size(), first + per);
+            if (first >= last) break;
+            threads.emplace_back([&, d, first, last]() {
+                try {
+                    // device d's own copy of the state (device 0 could share ref_data; a copy keeps it uniform)
+                    StateVectorT local(host.data(), host.size(), DevTag<int>{static_cast<int>(d), nullptr});
+                    std::vector<const plb200_obs *> hs;
+                    for (std::size_t o = first; o < last; o++) hs.push_back(obs[o]->handle());
+                    std::vector<double> out((last - first) * tp.size());
+                    PLB200_ABI(plb200_adjoint_jacobian(local.handle(), hs.data(), static_cast<int64_t>(hs.size()), &v,
+                                                       t.data(), static_cast<int64_t>(t.size()), apply_operations,
+                                                       out.data()));
+                    for (std::size_t i = 0; i < out.size(); i++) jac[first * tp.size() + i] = static_cast<PrecisionT>(out[i]);
+                } catch (...) {
+                    errors[d] = std::current_exception();
+                }
+            });
+        }
+        for (auto &th : threads) th.join();
+        for (auto &e : errors)
+            if (e) std::rethrow_exception(e);
     }
 };
 

@@ -310,7 +310,14 @@ template <class PrecisionT> void registerPrecision(py::module_ &m, const std::st
     py::class_<Adj>(alg, ("AdjointJacobianC" + bits).c_str(), py::module_local())
         .def(py::init<>())
         .def("__call__", call_adj, "Adjoint Jacobian method.")
-        .def("batched", call_adj, "Batch Adjoint Jacobian method.");
+        .def("batched", [](Adj &adj, const SV &svec, const std::vector<ObsPtr> &observables, const Ops &operations,
+                           const std::vector<std::size_t> &trainableParams) {
+            std::vector<PrecisionT> jac(observables.size() * trainableParams.size(), PrecisionT{0});
+            const JacobianData<SV> jd{operations.getTotalNumParams(), svec.getLength(), svec.getData(), observables,
+                                      operations, trainableParams};
+            adj.batchAdjointJacobian(std::span<PrecisionT>{jac}, jd, svec, false);
+            return py::array_t<PrecisionT>(py::cast(jac));
+        }, "Adjoint Jacobian with the observables split over the GPUs of the box.");
 }
 
 } // namespace

@@ -53,6 +53,13 @@ class NumpyEngine:
         out = [float(np.sum(p * (1 - 2 * ((idx >> (self.nloc - 1 - w)) & 1)))) for w in local_wires]
         return out + [float(p.sum())]
 
+    def pauli_sums(self, words, local_wires):
+        return np.array([self.sv.expval_pauli_word(w, ws) if w.strip("I") else float(np.vdot(self.sv.state, self.sv.state).real)
+                         for w, ws in zip(words, local_wires)])
+
+    def probs(self, local_wires=None):
+        return self.sv.probs(local_wires)
+
     def host_state(self):
         return self.sv.state.copy()
 
@@ -189,6 +196,74 @@ def run_ranks_multicall(world, n, seed, port):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=worker_multicall, args=(r, world, n, seed, port, "gloo", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    return res
+
+
+def worker_measure(rank, world, n, seed, port, backend, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    from pennylane_lightning_b200 import circuits
+    from pennylane_lightning_b200.dist import DistStateVector
+
+    try:
+        if backend == "nccl":
+            torch.cuda.set_device(rank)
+            os.environ["PLB200_JIT_MIN_QUBITS"] = "12"
+        sv = DistStateVector(n, np.complex128, engine_factory=NumpyEngine if backend == "gloo" else None)
+        sv.apply_ops(circuits.random_circuit(n, 3, seed), fuse=True)
+        co, words, wires = circuits.pauli_hamiltonian(n, 12, seed)
+        each = sv.expval_pauli_words(words, wires)
+        total = sv.expval_pauli_words(words, wires, co)
+        pw = [int(x) for x in np.random.default_rng(seed).permutation(n)[:4]]
+        p_sub = sv.probs(pw)
+        p_all = sv.probs()
+        samples = sv.generate_samples(4000, seed=11)
+        samples2 = sv.generate_samples(4000, seed=11)
+        full = sv.gather_state()
+        if rank == 0:
+            q.put(dict(each=each, total=total, pw=pw, p_sub=p_sub, p_all=p_all, samples=samples,
+                       same=bool(np.array_equal(samples, samples2)), state=full, words=words, wires=wires, co=co))
+    finally:
+        dist.destroy_process_group()
+
+
+def check_measurements(res, n):
+    from oracle import np_oracle
+
+    psi = res["state"]
+    ref = np_oracle.StateVector(n)
+    ref.set_state(psi)
+    for k, (w, ws) in enumerate(zip(res["words"], res["wires"])):
+        assert abs(res["each"][k] - ref.expval_pauli_word(w, ws)) < 1e-12
+    assert abs(res["total"] - sum(c * ref.expval_pauli_word(w, ws) for c, w, ws in zip(res["co"], res["words"], res["wires"]))) < 1e-12
+    np.testing.assert_allclose(res["p_sub"], ref.probs(res["pw"]), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res["p_all"], ref.probs(), rtol=0, atol=1e-13)
+    s = res["samples"]
+    assert s.shape == (4000, n) and res["same"]  # reproducible under a seed
+    idx = np.zeros(len(s), dtype=np.int64)
+    for w in range(n):
+        idx |= s[:, w].astype(np.int64) << (n - 1 - w)
+    emp = np.bincount(idx, minlength=1 << n) / len(s)
+    # total-variation distance of 4000 draws over 2^n outcomes: well below 0.25 for the right distribution
+    assert 0.5 * np.abs(emp - ref.probs()).sum() < 0.25
+    z0 = 1.0 - 2.0 * s[:, 0].mean()
+    assert abs(z0 - ref.expval_pauli_word("Z", [0])) < 0.08
+
+def run_ranks_measure(world, n, seed, backend="gloo", port=29680):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker_measure, args=(r, world, n, seed, port, backend, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=300)

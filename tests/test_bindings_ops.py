@@ -129,6 +129,11 @@ def test_adjoint_jacobian_binding(p):
     z = np.array([[1, 0], [0, -1]], dtype=dt)
     res = Adj().batched(sv, [H(z, [0])], o, [0])
     np.testing.assert_allclose(res, [-np.sin(0.3)], atol=1e-6)
+    # observable batching: with several GPUs every chunk of observables runs on its own device (one thread each);
+    # the rows must come back in order and equal the single-device sweep
+    many = [N("PauliZ", [0]), N("PauliZ", [1]), N("PauliX", [0]), N("PauliY", [1]), H(z, [1])]
+    np.testing.assert_allclose(Adj().batched(sv, many, o, [0, 1]), Adj()(sv, many, o, [0, 1]), atol=1e-6)
+    assert ops.DevPool.getTotalDevices() >= 1
 
 
 def test_full_flow_matches_reference(ref):

@@ -3,7 +3,7 @@ numpy local engine, against the single-process oracle on the same circuit."""
 import numpy as np
 import pytest
 
-from dist_helpers import mixed_circuit, multicall_tapes, run_ranks, run_ranks_multicall
+from dist_helpers import mixed_circuit, multicall_tapes, run_ranks, run_ranks_measure, run_ranks_multicall, check_measurements
 from oracle import np_oracle
 
 
@@ -70,3 +70,10 @@ def test_schedule_only_many_seeds():
                     sv.apply_ops(t)
                 maps.append(list(sv.phys))
             assert all(m == maps[0] for m in maps), (world, n, seed, maps)
+
+
+@pytest.mark.parametrize("world,n,seed", [(2, 7, 1), (4, 8, 2)])
+def test_sharded_measurements(world, n, seed):
+    """Pauli-word / Hamiltonian expval (X/Y on global wires are swapped in), probs marginals in the given wire
+    order, and sampling on the sharded state, against the single-process oracle on the gathered state."""
+    check_measurements(run_ranks_measure(world, n, seed, "gloo", port=29690 + seed), n)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from dist_helpers import mixed_circuit, run_ranks
+from dist_helpers import check_measurements, mixed_circuit, run_ranks, run_ranks_measure
 
 pytestmark = pytest.mark.gpu
 
@@ -34,3 +34,13 @@ def test_sharded_gpu_matches_single_gpu_and_reference(plb, ref, world, swap):
     assert res["swaps"] > 0
     if swap == "peer":
         assert res["fused_swaps"] == res["swaps"]  # every exchange rode on a pass's store phase
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_measurements_gpu(world):
+    """expval of Pauli words / a Hamiltonian (X, Y on global wires swapped in through a routed op-less pass),
+    probs marginals and sampling on a state sharded over GPUs."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n = 16
+    check_measurements(run_ranks_measure(world, n, 3, "nccl", port=29760 + world), n)
