@@ -206,6 +206,16 @@ class Observable:
         return cls(h)
 
     @classmethod
+    def sparse(cls, indptr, indices, data, wires=None):
+        """SparseHamiltonian: CSR matrix over the full 2^n index space (`wires` kept for signature parity)."""
+        h = C.c_void_p()
+        ip, ipp = _i64(indptr)
+        ix, ixp = _i64(indices)
+        d, dp = _c128(data)
+        _check(lib().plb200_obs_sparse(C.byref(h), ipp, ixp, dp, C.c_int64(len(ip) - 1)))
+        return cls(h)
+
+    @classmethod
     def tensor(cls, terms):
         h = C.c_void_p()
         arr = (C.c_void_p * len(terms))(*[t._h for t in terms])

@@ -383,7 +383,9 @@ void probs_impl(StateVec &s, const int64_t *wires, int64_t nw, double *out) {
 
 // Alias-method sampler, reproducing DiscreteRandomVariable (MeasurementKernels.hpp:308-381)
 // and Measurements::generate_samples (MeasurementsLQubit.hpp:662-679) step for step, including
-// the arithmetic type of every intermediate, so that a shared seed gives identical samples.
+// the arithmetic type of every intermediate, so that a shared seed gives identical samples for identical
+// probabilities (marginals over <= 11 wires come from an atomically accumulated histogram whose last bits can vary
+// run to run; a bucket comparison can then flip in the rare case of a tie at the last bit).
 template <typename P>
 void alias_samples(const std::vector<double> &probs_d, int64_t n_wires, int64_t shots, std::mt19937 &gen,
                    uint64_t *out) {

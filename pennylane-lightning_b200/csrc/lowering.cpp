@@ -432,10 +432,15 @@ std::vector<COp> lower_matrix(int64_t n, const std::vector<cd> &matrix,
         d.tbits = wires_to_tbits(n, wires);
         d.cmask = cmask, d.cval = cval;
         d.mat = inverse ? dagger(matrix, static_cast<int>(dim)) : matrix;
+        PLB_CHECK(d.k() <= 11, "applyMatrix: dense matrices on more than 11 wires are not supported");
         return {d};
     }
-    return analyse(inverse ? dagger(matrix, static_cast<int>(dim)) : matrix, wires_to_tbits(n, wires),
-                   cmask, cval, false);
+    auto ops = analyse(inverse ? dagger(matrix, static_cast<int>(dim)) : matrix, wires_to_tbits(n, wires), cmask, cval, false);
+    // the dense kernels stage a 2^k column in shared memory: reject what cannot execute HERE (validation time),
+    // not after the matrix has been copied to the device
+    for (const COp &op : ops)
+        PLB_CHECK(op.kind != OP_DENSE || op.k() <= 11, "applyMatrix: dense matrices on more than 11 wires are not supported");
+    return ops;
 }
 
 std::vector<COp> lower_gate(int64_t n, const GateCall &g) {

@@ -3,7 +3,10 @@
 // launch), small-matrix expval, Pauli-sum (Hamiltonian) application, state preparation helpers
 // and the local half of the distributed index-bit swap.
 // All sums accumulate in fp64 per thread, reduce by warp shuffle, then by a fixed-order second
-// stage -> deterministic for a given launch shape.
+// stage -> deterministic for a given launch shape.  Two exceptions accumulate with fp64 atomics and are NOT bitwise
+// reproducible run to run (the order of the additions varies): probs_hist_kernel (marginals over <= 11 wires:
+// shared-memory histogram per CTA, then global atomics) and the overlap accumulators of the fused adjoint passes
+// (fusion.cu).  Their results agree with the reference to the stated tolerance, not to the last bit.
 #include <type_traits>
 
 #include "device.cuh"
