@@ -224,6 +224,40 @@ __global__ void __launch_bounds__(kThreads)
 // <psi| Z-word |psi> for up to W diagonal words in ONE read of the state:
 // sum_i |a_i|^2 (-1)^{popcount(i & z_q)}, q < W  (expval of PauliZ on every wire, ZZ terms of an Ising
 // Hamiltonian, ...).  partials laid out [block][W].
+// <Z_b> for EVERY index bit b and the norm in ONE read of the state (e2e: expval(PauliZ(w)) for all wires).  The
+// grid has a power-of-two number of threads 2^s and strides by it, so the low s index bits are constant per thread:
+// for those a thread needs only its total, the sign is applied once at the end; only the n - s high bits vary inside
+// the loop (they are the loop counter's bits) and get an accumulator each: total - 2 * (sum over set bit).
+constexpr int kZAllMaxBits = 40, kZAllMaxHigh = 16;
+template <typename T2>
+__global__ void __launch_bounds__(kThreads)
+    zall_kernel(const T2 *__restrict__ a, int n, int s, double *partials) {
+    const uint64_t gtid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t iters = uint64_t{1} << (n - s);
+    double total = 0.0, hi[kZAllMaxHigh];
+#pragma unroll
+    for (int j = 0; j < kZAllMaxHigh; j++) hi[j] = 0.0;
+#pragma unroll 4
+    for (uint64_t k = 0; k < iters; k++) {
+        const T2 x = a[(k << s) | gtid];
+        const double p = static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+        total += p;
+#pragma unroll
+        for (int j = 0; j < kZAllMaxHigh; j++)
+            if ((k >> j) & 1) hi[j] += p;
+    }
+    double v[kZAllMaxBits + 1];
+#pragma unroll
+    for (int b = 0; b <= kZAllMaxBits; b++) {
+        double r = 0.0;
+        if (b < s) r = ((gtid >> b) & 1) ? -total : total;
+        else if (b < n) r = total - 2.0 * hi[(b - s) < kZAllMaxHigh ? (b - s) : 0];
+        else if (b == kZAllMaxBits) r = total; // the norm travels in the last slot
+        v[b] = r;
+    }
+    block_reduce_store<kZAllMaxBits + 1>(v, partials + static_cast<size_t>(blockIdx.x) * (kZAllMaxBits + 1));
+}
+
 template <int W> struct ZMasks {
     uint64_t z[W];
 };
@@ -613,6 +647,29 @@ void pauli_inner(StateVec &a, const StateVec &b, const PauliWordMask *words, int
     bool all_diag = a.data == b.data;
     for (int64_t k = 0; k < n_words && all_diag; k++)
         all_diag = words[k].x == 0 && words[k].cmask == 0 && words[k].ny == 0;
+    if (all_diag && n_words > 8 && a.n <= kZAllMaxBits) {
+        // every word a single Z (or the identity): all <Z_b> + the norm from ONE sweep (zall_kernel)
+        bool singles = true;
+        for (int64_t k = 0; k < n_words && singles; k++) singles = __builtin_popcountll(words[k].z) <= 1;
+        int s = static_cast<int>(std::min<int64_t>(a.n, 19)); // 2^19 threads
+        while (a.n - s > kZAllMaxHigh) s++;
+        if (singles && s >= 8) {
+            const int nb = 1 << (s - 8); // kThreads = 2^8
+            constexpr int NV = kZAllMaxBits + 1;
+            double *part = a.reduce_buf(static_cast<size_t>(NV) * nb + NV + 8);
+            DISPATCH(a, (zall_kernel<T2><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), static_cast<int>(a.n), s, part)),
+                     (zall_kernel<T2><<<nb, kThreads, 0, a.stream>>>(static_cast<const T2 *>(a.data), static_cast<int>(a.n), s, part)));
+            a.launches++;
+            PLB_CUDA(cudaGetLastError());
+            double r[NV];
+            finish_reduce<NV>(a, part, 1, nb, r);
+            for (int64_t k = 0; k < n_words; k++) {
+                out[2 * k] = words[k].z ? r[__builtin_ctzll(words[k].z)] : r[kZAllMaxBits];
+                out[2 * k + 1] = 0.0;
+            }
+            return;
+        }
+    }
     if (all_diag && n_words > 1) {
         // 8 words per read of the state, or 32 when there are many (<Z_w> on every wire of a 30-qubit register
         // is ONE sweep instead of four)

@@ -487,7 +487,10 @@ class DistStateVector:
         for i, op in enumerate(rest):
             for w in self._nondiag_targets(op):
                 nxt.setdefault(w, i)
-        need = need[: self.g]
+        # at most PLB200_SWAP_MAX_BITS wires per exchange (default: all g global bits).  A routed 1-bit exchange sends
+        # S/2 per GPU and hides behind the pass that carries it; a 3-bit one sends 7S/8 and does not — fewer, larger
+        # exchanges are not always cheaper
+        need = need[: max(1, min(self.g, int(os.environ.get("PLB200_SWAP_MAX_BITS", "3"))))]
         cand = [w for w in range(self.n) if not self._is_global(w) and w not in need]
         # the wires on the lowest local bits are evicted last (the sort key puts them behind every other
         # candidate): swapping a bit below the 128-B line splits every line (323 vs 692 GB/s measured)

@@ -254,13 +254,23 @@ def test_lazy_gate_queue(p, ref):
     pr = np.asarray(m.probs([0, 1]))
     assert sv.pendingOps() == 0
     np.testing.assert_allclose(pr, r.probs([0, 1]), atol=1e-12 if p == "128" else 1e-5)
-    # a full-state preparation discards pending gates; applyMatrix keeps program order (flushes first)
+    # a full-state preparation discards pending gates; small matrices and Pauli rotations JOIN the queue in program
+    # order (validated at call time), larger matrices flush it and run at once
     sv.PauliX([1], False, [])
     sv.resetStateVector()
     assert sv.pendingOps() == 0 and np.isclose(state(sv, dt)[0], 1.0)
     sv.PauliX([n - 1], False, [])  # |0..01>
     sv.applyMatrix(np.array([[0, 1], [1, 0]], dtype=dt), [n - 2], False)  # |0..11>
     sv.PauliX([n - 1], False, [])  # |0..10>
-    assert sv.pendingOps() == 1
+    sv.applyPauliRot([0, n - 1], False, [np.pi], "XI")  # -i X on wire 0
+    assert sv.pendingOps() == 4
+    with pytest.raises(RuntimeError):  # a bad call still fails when it is made, not at the flush
+        sv.applyMatrix(np.eye(2, dtype=dt), [n + 3], False)
+    assert sv.pendingOps() == 4
     out = state(sv, dt)
-    assert np.isclose(out[2], 1.0) and np.isclose(np.abs(out).sum(), 1.0)
+    assert sv.pendingOps() == 0
+    assert np.isclose(abs(out[2 + (1 << (n - 1))]), 1.0) and np.isclose(np.abs(out).sum(), 1.0)
+    big = np.eye(32, dtype=dt)[::-1].copy()  # 5 wires: flushes, then runs at once (tensor-core path)
+    sv.PauliX([0], False, [])
+    sv.applyMatrix(big, [1, 2, 3, 4, 5], False)
+    assert sv.pendingOps() == 0

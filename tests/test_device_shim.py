@@ -180,7 +180,10 @@ def test_shim_call_order_with_stub_pennylane(plb, ref, dtype, monkeypatch):
     np.testing.assert_allclose(sv.state, r.get_state(), rtol=0, atol=tol)
     # measurements: fused Pauli sentence
     meas = mm.LightningB200Measurements(sv)
-    word = lambda w, ws: types.SimpleNamespace(word=w, wires=np.array(ws))
+    class word:  # stands for a qml.pauli.PauliWord: hashable, has .wires
+        def __init__(self, w, ws):
+            self.word, self.wires = w, np.array(ws)
+
     mp = types.SimpleNamespace(obs=types.SimpleNamespace(pauli_rep={word("XZ", [0, 2]): 0.5, word("Y", [1]): -1.5}))
     want = 0.5 * r.expval(ref.Observable.tensor([ref.Observable.named("PauliX", [0], dtype=dtype),
                                                  ref.Observable.named("PauliZ", [2], dtype=dtype)])) - 1.5 * r.expval(

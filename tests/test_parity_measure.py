@@ -130,6 +130,25 @@ def test_diagonal_words_single_pass(plb, ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [9, 13, 21, 24])
+def test_all_z_expvals_one_sweep(plb, ref, dtype, n):
+    """<Z_w> on every wire (+ the norm through an identity word) takes the one-sweep kernel: the low index bits
+    are constant per thread, only the high ones get accumulators.  Sizes below / at / above the 2^19-thread grid."""
+    a, b = plb.StateVector(n, dtype), ref.StateVector(n, dtype)
+    ops = circuits.random_circuit(n, 2, 31)
+    a.apply_ops(ops), b.apply_ops(ops)
+    order = [int(w) for w in np.random.default_rng(n).permutation(n)]
+    words, wires = ["Z"] * n + ["I"], [[w] for w in order] + [[0]]
+    l0 = a.kernel_launches
+    each = a.expval_pauli_words_each(words, wires)
+    assert a.kernel_launches - l0 <= 2  # one sweep + the final reduction
+    tol = 10 * TOL[np.dtype(dtype)]
+    for k, w in enumerate(order):
+        assert abs(each[k] - b.expval_named("PauliZ", [w])) < tol, (k, w)
+    assert abs(each[n] - 1.0) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_state_preparation(plb, ref, dtype):
     n = 6
     tol = TOL[np.dtype(dtype)]
