@@ -115,19 +115,18 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
 int64_t g_emu_jit_passes = 0;
 template <typename T2, class Cfg>
 bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp, const jit::Route &route = jit::Route{},
-                      const jit::RouteParams<T2> *rp = nullptr) {
-    if constexpr (Cfg::NS != 1) return false;
-    else {
+                      const jit::RouteParams<T2> *rp = nullptr, T2 *sv1 = nullptr, double *acc = nullptr) {
+    {
         const std::string src = jit::generate_pass_source<T2, Cfg>(pp, route);
         if (src.empty()) return false;
-        static std::map<uint64_t, void (*)(void *, const void *, const void *)> cache;
+        static std::map<uint64_t, void (*)(void *, const void *, const void *, void *, double *)> cache;
         const uint64_t key = jit::fnv1a(src) ^ (static_cast<uint64_t>(src.size()) << 40);
         auto it = cache.find(key);
         if (it == cache.end()) {
             const char *dir = std::getenv("PLB200_EMU_JIT_DIR");
             static int serial = 0; // one counter per instantiation: the precision tag keeps the names apart
             const std::string base = std::string(dir ? dir : "/tmp") + "/plb_jit_" + std::to_string(::getpid()) + "_" +
-                                     (sizeof(T2) == 16 ? "d" : "f") + std::to_string(serial++);
+                                     (sizeof(T2) == 16 ? "d" : "f") + (Cfg::NS == 2 ? "a" : "") + std::to_string(serial++);
             {
                 std::ofstream o(base + ".cpp");
                 o << src;
@@ -136,7 +135,7 @@ bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp, const jit::Route &route
             if (std::system(cmd.c_str()) != 0) fail("emu jit: g++ failed on " + base + ".cpp");
             void *h = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
             if (!h) fail(std::string("emu jit: dlopen failed: ") + dlerror());
-            auto fn = reinterpret_cast<void (*)(void *, const void *, const void *)>(dlsym(h, "plb_pass_host"));
+            auto fn = reinterpret_cast<void (*)(void *, const void *, const void *, void *, double *)>(dlsym(h, "plb_pass_host"));
             if (!fn) fail("emu jit: plb_pass_host missing");
             it = cache.emplace(key, fn).first;
             if (!std::getenv("PLB200_EMU_JIT_KEEP")) {
@@ -145,7 +144,7 @@ bool emulate_pass_jit(T2 *sv0, const PassParams<T2> &pp, const jit::Route &route
             }
         }
         const jit::RouteParams<T2> none{};
-        it->second(sv0, &pp, rp ? rp : &none);
+        it->second(sv0, &pp, rp ? rp : &none, sv1, acc);
         g_emu_jit_passes++;
         return true;
     }
@@ -980,6 +979,7 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
     using Cfg = AdjCfg<T2>;
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
     prepare_kernel<T2, Cfg>(lambda.device);
+    const bool use_jit = jit::mode() != jit::Mode::Off && lambda.n >= jit::min_qubits();
     // device accumulators: one slab of kMaxPassOps doubles per tile pass; a pass executes >= 2 items
     const size_t max_pass = items.size() / 2 + 1;
     const size_t acc_bytes = max_pass * kMaxPassOps * sizeof(double);
@@ -1006,8 +1006,15 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
             return;
         }
         if (st.op == -2) fail("fusion: adjoint passes carry no scalar across passes");
-        launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data),
-                             dacc + passes.size() * kMaxPassOps, *pp);
+        double *pacc = dacc + passes.size() * kMaxPassOps;
+        jit::Kernel k;
+        if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
+        if (k) {
+            void *a0 = lambda.data, *a1 = hl.data;
+            void *args[4] = {&a0, &a1, &pacc, const_cast<PassParams<T2> *>(pp)};
+            jit::launch_args(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), lambda.stream, args);
+        } else
+            launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data), pacc, *pp);
         lambda.launches++;
         passes.push_back({st.slots, st.slot_scale});
         stats[0]++;
@@ -1141,7 +1148,7 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
             return;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if (std::getenv("PLB200_EMU_JIT") && emulate_pass_jit<T2, Cfg>(sv0, *pp)) {
+        if (std::getenv("PLB200_EMU_JIT") && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
         } else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
         else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];

@@ -157,6 +157,18 @@ DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) 
     cmul_ip(a, m2);
     cmul_ip(b, m3);
 }
+// adjoint (two-state) passes: Im / Re of conj(a) b in double, and the per-CTA overlap accumulators
+DEV double im_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.y - (double)a.y * (double)b.x; }
+DEV double re_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.x + (double)a.y * (double)b.y; }
+#if defined(PLB_JIT_HOST)
+DEV void ovl_reduce(double *acc, int slot, double s) { acc[slot] += s; }
+#else
+DEV void ovl_reduce(double *acc, int slot, double s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc[slot], s);
+}
+#endif
 DEV u64 insert_bits_m(u64 x, const BitInsert &bi) {
 #pragma unroll
     for (int i = 0; i < PLB_M; i++) {
@@ -223,7 +235,8 @@ template <typename T2> struct alignas(16) RouteParams {
 };
 
 template <typename T2, class Cfg> class Gen {
-    static constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NV = 1 << R, NTB = M - R;
+    static constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NV = 1 << R, NTB = M - R, NS = Cfg::NS;
+    char cur_set = 'v'; // register set statements are emitted for: 'v' (lambda / the state), 'h' (H lambda, NS == 2)
     const PassParams<T2> &pp;
     std::string s;
     int perm[NV]; // logical register u lives in variable v<perm[u]>
@@ -241,7 +254,8 @@ template <typename T2, class Cfg> class Gen {
         snprintf(b, sizeof(b), "0x%xu", v);
         return b;
     }
-    std::string V(int u) const { return "v" + std::to_string(perm[u]); }
+    std::string V(int u) const { return std::string(1, cur_set) + std::to_string(perm[u]); }
+    std::string Vs(char set, int u) const { return std::string(1, set) + std::to_string(perm[u]); }
 
     // condition of op K: tile-uniform part (outside controls) and thread part
     std::string cond_of(const TileOp<T2> &op, int K) const {
@@ -277,7 +291,7 @@ template <typename T2, class Cfg> class Gen {
     // full 128-byte line per access.  The scheduler arranges that for the first and the last round of a pass
     // whenever none of those bits is a register bit (fusion.cu, thread-bit assignment).
     bool direct_ok(int r) const {
-        if (std::getenv("PLB200_JIT_NO_DIRECT")) return false;
+        if (NS == 2 || std::getenv("PLB200_JIT_NO_DIRECT")) return false;
         int tpos[NTB], rl[R];
         round_bits(round_hdr(r), tpos, rl);
         for (int i = 0; i < LOW; i++)
@@ -309,8 +323,11 @@ template <typename T2, class Cfg> class Gen {
         int tpos[NTB], rl[R];
         round_bits(rh, tpos, rl);
         const bool routed = to_global && route.k > 0;
-        add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, T2 *__restrict__ sv%s) {\n", r,
-            routed ? ", const RouteParams &rp" : "");
+        if (NS == 2)
+            add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, unsigned char *smem1, double *acc) {\n", r);
+        else
+            add("DEV void round_%d(const PassParams &pp, const u32 tid, const u64 base, unsigned char *smem, T2 *__restrict__ sv%s) {\n", r,
+                routed ? ", const RouteParams &rp" : "");
         const uint32_t lowmask = ((1u << Swz<T2>::B) - 1u) * static_cast<uint32_t>(sizeof(T2));
         std::vector<uint32_t> lows;
         auto low_id = [&](uint32_t low) {
@@ -326,8 +343,10 @@ template <typename T2, class Cfg> class Gen {
             for (int i = 0; i < NTB; i++) add(" ^ ((tid >> %d & 1u) * %s)", i, hex(rh.w[i]).c_str());
             s += ";\n";
             for (int u = 0; u < NV; u++) low_id(rh.sroff[u] & lowmask);
-            for (size_t i = 0; i < lows.size(); i++)
+            for (size_t i = 0; i < lows.size(); i++) {
                 add("    unsigned char *const b%zu = smem + (sb ^ %s);\n", i, hex(lows[i]).c_str());
+                if (NS == 2) add("    unsigned char *const c%zu = smem1 + (sb ^ %s);\n", i, hex(lows[i]).c_str());
+            }
         }
         if (from_global || to_global) {
             // element offset of this thread inside the tile (global index bits) and of each register
@@ -347,6 +366,8 @@ template <typename T2, class Cfg> class Gen {
             if (from_global) add("    T2 v%d = gp[%s];\n", u, greg(u).c_str());
             else
                 add("    T2 v%d = *(const T2 *)(b%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
+            if (NS == 2)
+                add("    T2 h%d = *(const T2 *)(c%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
         }
         // thread-scalar diagonal factors of this round (K_DIAG_T / K_DIAG1_T): merged when there are >= 2
         int n_tscalar = 0;
@@ -357,11 +378,26 @@ template <typename T2, class Cfg> class Gen {
         const bool merge_ts = n_tscalar >= 2;
         if (merge_ts) s += "    T2 ts; ts.x = (real)1; ts.y = (real)0; bool ts_any = false;\n";
 
-        for (int k = 0; k < rh.nops; k++) gen_op(rh.first_op + k, merge_ts);
+        for (int k = 0; k < rh.nops; k++) {
+            const int K = rh.first_op + k;
+            if (pp.ops[K].code & F_OVL) {
+                gen_overlap(K);
+                continue;
+            }
+            if (NS == 2) { // H lambda first, as the interpreter does; renamings / the thread scalar happen once
+                cur_set = 'h';
+                gen_op(K, merge_ts, false);
+                cur_set = 'v';
+            }
+            gen_op(K, merge_ts, true);
+        }
 
         if (merge_ts) {
             s += "    if (ts_any) {\n";
-            for (int u = 0; u < NV; u++) add("        cmul_ip(%s, ts);\n", V(u).c_str());
+            for (int u = 0; u < NV; u++) {
+                add("        cmul_ip(%s, ts);\n", Vs('v', u).c_str());
+                if (NS == 2) add("        cmul_ip(%s, ts);\n", Vs('h', u).c_str());
+            }
             s += "    }\n";
         }
         gen_ladders(rh);
@@ -411,8 +447,47 @@ template <typename T2, class Cfg> class Gen {
             } else if (to_global) add("    gp[%s] = %s;\n", greg(u).c_str(), V(u).c_str());
             else
                 add("    *(T2 *)(b%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), V(u).c_str());
+            if (NS == 2)
+                add("    *(T2 *)(c%d + %s) = %s;\n", low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str(), Vs('h', u).c_str());
         }
         s += "}\n";
+    }
+
+    // adjoint: thread-local contribution to Im<H lambda| G |lambda> of one overlap op, reduced per warp into the
+    // CTA's accumulator (tile_exec.cuh overlap_op); l = the 'v' registers, h = the 'h' registers
+    void gen_overlap(int K) {
+        const TileOp<T2> &op = pp.ops[K];
+        const int kind = code_kind(op.code), p = code_p(op.code);
+        const std::string O = "pp.ops[" + std::to_string(K) + "]";
+        add("    { // overlap op %d kind %d P %d slot %u\n", K, kind, p, op.slot);
+        const bool out_cond = (op.code & F_COND) && op.cmask_o;
+        if (out_cond) s += "        if ((base & " + O + ".cmask_o) == " + O + ".cval_o) {\n";
+        s += "        double ovl = 0.0;\n";
+        const bool thr_cond = (op.code & F_COND) && op.cm_tid;
+        if (thr_cond) s += "        if ((tid & " + hex(op.cm_tid) + ") == " + hex(op.cv_tid) + ") {\n";
+        if (kind == K_OVL_D) {
+            const std::string par = (op.code & F_PAR) ? par_of(op, K) : std::string();
+            add("        const double g0 = (double)%s.m[0].x, g1 = (double)%s.m[0].y;\n", O.c_str(), O.c_str());
+            if (par.empty()) s += "        const double gE = g0, gO = g1;\n";
+            else s += "        const bool pt = " + par + ";\n        const double gE = pt ? g1 : g0, gO = pt ? g0 : g1;\n";
+            for (int u = 0; u < NV; u++)
+                if ((op.umask >> u) & 1u)
+                    add("        ovl += %s * im_cb(%s, %s);\n", ((op.upar >> u) & 1u) ? "gO" : "gE", Vs('h', u).c_str(), Vs('v', u).c_str());
+        } else {
+            std::vector<std::pair<int, int>> pr;
+            pairs_on(p, pr);
+            for (auto [u0, u1] : pr) {
+                if (!((op.umask >> u0) & 1u)) continue;
+                if (kind == K_OVL_Y)
+                    add("        ovl += re_cb(%s, %s) - re_cb(%s, %s);\n", Vs('h', u1).c_str(), Vs('v', u0).c_str(), Vs('h', u0).c_str(), Vs('v', u1).c_str());
+                else
+                    add("        ovl += im_cb(%s, %s) + im_cb(%s, %s);\n", Vs('h', u0).c_str(), Vs('v', u1).c_str(), Vs('h', u1).c_str(), Vs('v', u0).c_str());
+            }
+        }
+        if (thr_cond) s += "        }\n";
+        add("        ovl_reduce(acc, %u, ovl);\n", op.slot);
+        if (out_cond) s += "        }\n";
+        s += "    }\n";
     }
 
     // pairs (u0, u1) on register bit P
@@ -424,7 +499,7 @@ template <typename T2, class Cfg> class Gen {
         }
     }
 
-    void gen_op(int K, bool merge_ts) {
+    void gen_op(int K, bool merge_ts, bool last) {
         const TileOp<T2> &op = pp.ops[K];
         const uint32_t code = op.code;
         const int kind = code_kind(code), P = code_p(code), C = static_cast<int>((code >> 16) & 7u);
@@ -491,8 +566,9 @@ template <typename T2, class Cfg> class Gen {
                     pr.emplace_back(u0, u1);
                 }
             }
-            if (cond.empty()) { // a renaming: no instructions
-                for (auto [a, b] : pr) std::swap(perm[a], perm[b]);
+            if (cond.empty()) { // a renaming: no instructions (once for both register sets)
+                if (last)
+                    for (auto [a, b] : pr) std::swap(perm[a], perm[b]);
                 s += "        // register renaming\n";
             } else {
                 open_cond();
@@ -531,7 +607,9 @@ template <typename T2, class Cfg> class Gen {
             std::string c2 = cond;
             if (kind == K_DIAG1_T) c2 = c2.empty() ? "pt" : "(" + c2 + ") && pt";
             if (!c2.empty()) s += "        if (" + c2 + ") {\n";
-            if (kind != K_DIAG_CT && merge_ts) s += "            cmul_ip(ts, d); ts_any = true;\n";
+            if (kind != K_DIAG_CT && merge_ts) {
+                if (last) s += "            cmul_ip(ts, d); ts_any = true;\n";
+            }
             else
                 for (int u = 0; u < NV; u++) {
                     if (kind == K_DIAG_CT && !((u >> P) & 1)) continue;
@@ -575,7 +653,10 @@ template <typename T2, class Cfg> class Gen {
             }
             s += "        if (any) {\n";
             for (int u = 0; u < NV; u++)
-                if (p >= R || ((u >> p) & 1)) add("            cmul_ip(%s, t);\n", V(u).c_str());
+                if (p >= R || ((u >> p) & 1)) {
+                    add("            cmul_ip(%s, t);\n", Vs('v', u).c_str());
+                    if (NS == 2) add("            cmul_ip(%s, t);\n", Vs('h', u).c_str());
+                }
             s += "        }\n    }\n";
             q += 1 + (n + per - 1) / per;
         }
@@ -583,12 +664,67 @@ template <typename T2, class Cfg> class Gen {
 
     // resident CTAs per SM the kernel is compiled for (register cap); PLB200_JIT_MINB overrides (tuning)
     static int minb() {
-        const char *e = std::getenv("PLB200_JIT_MINB");
+        const char *e = std::getenv(NS == 2 ? "PLB200_JIT_ADJ_MINB" : "PLB200_JIT_MINB");
         const int v = e ? std::atoi(e) : 0;
         // measured on the 30-qubit benchmark tape: the specialised code wants 128 registers (no spills; ptxas
         // takes 202 uncapped): c128 4 CTAs x 128 threads 211 ms (5: 232, 6: 282 with 0.5 KB of spills per
         // thread), c64 2 CTAs x 256 threads 143 ms (3: 155, 4: 264)
         return v > 0 ? v : std::max(1, 512 / (1 << NTB));
+    }
+
+    // drivers of an adjoint pass: two tiles travel together, overlaps accumulate per CTA in shared memory and are
+    // flushed once per CTA with fp64 atomics (as tile_kernel does)
+    void gen_two_state_drivers(int nr) {
+        std::string dev, host;
+        for (int r = 0; r < nr; r++) {
+            const std::string call = "round_" + std::to_string(r) + "(pp, tid, base, smem, smem1, acc)";
+            dev += "        " + call + "; __syncthreads();\n";
+            host += "        for (u32 tid = 0; tid < PLB_NT; tid++) { " + call + "; }\n";
+        }
+        s += "#if defined(PLB_JIT_HOST)\n"
+             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp, const RouteParams *, T2 *sv1, double *acc) {\n"
+             "    const PassParams &pp = *ppp;\n"
+             "    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)], smem1[(sizeof(T2) << PLB_M)];\n"
+             "    static u64 goff[1 << (PLB_M - PLB_LOW)];\n"
+             "    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);\n"
+             "    for (u64 t = 0; t < pp.hdr.ntiles; t++) {\n"
+             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n"
+             "        for (u32 tid = 0; tid < PLB_NT; tid++) { load_tile(tid, base, goff, sv, smem); load_tile(tid, base, goff, sv1, smem1); }\n" +
+             host +
+             "        for (u32 tid = 0; tid < PLB_NT; tid++) { store_tile(tid, base, goff, sv, smem); store_tile(tid, base, goff, sv1, smem1); }\n"
+             "    }\n}\n"
+             "#else\n"
+             "extern \"C\" __global__ void __launch_bounds__(PLB_NT, PLB_MINB)\n"
+             "    plb_pass(T2 *__restrict__ sv, T2 *__restrict__ sv1, double *__restrict__ acc_g, const __grid_constant__ PassParams pp) {\n"
+             "    extern __shared__ __align__(16) unsigned char smem[];\n"
+             "    unsigned char *smem1 = smem + (sizeof(T2) << PLB_M);\n"
+             "    u64 *goff = (u64 *)(smem + 2 * (sizeof(T2) << PLB_M));\n"
+             "    double *acc = (double *)(goff + (1 << (PLB_M - PLB_LOW)));\n"
+             "    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);\n"
+             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT) acc[i] = 0.0;\n"
+             "    __syncthreads();\n"
+             "    const u32 tid = threadIdx.x;\n"
+             "    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {\n"
+             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n"
+             "        if (t + gridDim.x < pp.hdr.ntiles) {\n"
+             "            const u64 nbase = insert_bits_m(t + gridDim.x, pp.hdr.tile_ins);\n"
+             "            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT) {\n"
+             "                asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(sv + (nbase | goff[l])));\n"
+             "                asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(sv1 + (nbase | goff[l])));\n"
+             "            }\n"
+             "        }\n"
+             "        load_tile(tid, base, goff, sv, smem);\n"
+             "        load_tile(tid, base, goff, sv1, smem1);\n"
+             "        __syncthreads();\n" +
+             dev +
+             "        store_tile(tid, base, goff, sv, smem);\n"
+             "        store_tile(tid, base, goff, sv1, smem1);\n"
+             "        __syncthreads();\n"
+             "    }\n"
+             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT)\n"
+             "        if (acc[i] != 0.0) atomicAdd(&acc_g[i], acc[i]);\n"
+             "}\n"
+             "#endif\n";
     }
 
   public:
@@ -622,6 +758,10 @@ template <typename T2, class Cfg> class Gen {
             }
         }
         for (int r = 0; r < nr; r++) gen_round(r, r == 0 && first_direct, r == nr - 1 && last_direct);
+        if (NS == 2) {
+            gen_two_state_drivers(nr);
+            return s;
+        }
         // ---- the two drivers: the device kernel and the test-only host loop (phases separated by barriers on
         // the device are completed for every thread before the next phase starts on the host)
         std::string dev, host;
@@ -638,7 +778,7 @@ template <typename T2, class Cfg> class Gen {
         }
         if (!last_direct) phase("store_tile(tid, base, goff, sv, smem)", !first_direct || nr == 1);
         s += "#if defined(PLB_JIT_HOST)\n"
-             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp, const RouteParams *rpp) {\n"
+             "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp, const RouteParams *rpp, T2 *, double *) {\n"
              "    const PassParams &pp = *ppp;\n"
              "    const RouteParams &rp = *rpp; (void)rp;\n"
              "    alignas(16) static unsigned char smem[(sizeof(T2) << PLB_M)];\n"
@@ -675,7 +815,6 @@ template <typename T2, class Cfg> class Gen {
 // does not cover (the interpreter kernel then runs it).
 template <typename T2, class Cfg>
 std::string generate_pass_source(const PassParams<T2> &pp, const Route &route = Route{}) {
-    static_assert(Cfg::NS == 1, "forward passes only");
     Gen<T2, Cfg> g(pp, route);
     std::string src = g.run();
     return g.ok ? src : std::string();

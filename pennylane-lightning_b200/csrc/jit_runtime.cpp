@@ -362,6 +362,12 @@ void launch(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, v
     if (rc != 0) fail("JIT pass kernel launch failed: " + cu_err(rc));
 }
 
+void launch_args(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void **args) {
+    const int rc = driver().LaunchKernel(static_cast<CUfunction>(k.fn), grid, 1, 1, block, 1, 1, static_cast<unsigned>(smem_bytes),
+                                         static_cast<CUstream>(stream), args, nullptr);
+    if (rc != 0) fail("JIT pass kernel launch failed: " + cu_err(rc));
+}
+
 void wait_idle() {
     std::unique_lock<std::mutex> lk(g_mu);
     g_cv_idle.wait(lk, [] { return g_queue.empty() && g_inflight == 0; });

@@ -25,6 +25,8 @@ struct Kernel {
 Kernel lookup(const std::string &src, int device, size_t smem_bytes, bool force_sync = false);
 void launch(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void *sv,
             const void *pass_params, const void *route_params = nullptr);
+// generic form: args[] as cuLaunchKernel takes them (adjoint passes: two states + accumulators + description)
+void launch_args(const Kernel &k, unsigned grid, unsigned block, size_t smem_bytes, void *stream, void **args);
 void wait_idle();
 // {compiled, loaded from disk, launches of compiled kernels, launches left to the interpreter, failed,
 //  compile microseconds, queued + in flight, structures seen}

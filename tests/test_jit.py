@@ -170,3 +170,25 @@ def test_jit_same_kernel_other_angles(plb, ref, jit_sync):
     r = ref.StateVector(n)
     r.apply_ops(ops2)
     np.testing.assert_allclose(b.get_state(), r.get_state(), rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_jit_adjoint_passes_match_reference(plb, ref, jit_sync, dtype):
+    """The fused adjoint sweep (two-state passes with in-register generator overlaps) through specialised kernels."""
+    n = 16
+    ops, tp = circuits.hardware_efficient_ansatz(n, 120, 5)
+    co, words, wires = circuits.pauli_hamiltonian(n, 10, 5)
+    a, r = plb.StateVector(n, dtype), ref.StateVector(n, dtype)
+    ham_a = circuits.hamiltonian_observable(plb, co, words, wires)
+    ham_r = circuits.hamiltonian_observable(ref, co, words, wires, dtype=dtype)
+    before = plb.jit_stats()
+    ja = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
+    after = plb.jit_stats()
+    assert after["jit_launches"] > before["jit_launches"] and after["failed"] == before["failed"]
+    jr = r.adjoint_jacobian([ham_r], ops, tp, apply_ops=True)
+    np.testing.assert_allclose(ja, jr, rtol=0, atol=1e-11 if dtype == np.complex128 else 2e-4)
+    plb.jit_set_mode(0)
+    ji = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
+    plb.jit_set_mode(2)
+    np.testing.assert_allclose(ja, ji, rtol=0, atol=1e-11 if dtype == np.complex128 else 2e-4)

@@ -134,18 +134,22 @@ def test_diagonal_words_single_pass(plb, ref, dtype):
 def test_all_z_expvals_one_sweep(plb, ref, dtype, n):
     """<Z_w> on every wire (+ the norm through an identity word) takes the one-sweep kernel: the low index bits
     are constant per thread, only the high ones get accumulators.  Sizes below / at / above the 2^19-thread grid."""
-    a, b = plb.StateVector(n, dtype), ref.StateVector(n, dtype)
+    a = plb.StateVector(n, dtype)
     ops = circuits.random_circuit(n, 2, 31)
-    a.apply_ops(ops), b.apply_ops(ops)
+    a.apply_ops(ops)
+    # the reference evaluates the SAME amplitudes in double precision (lightning.qubit's c64 reductions accumulate
+    # in float: at 2^24 amplitudes its own <Z> is only good to ~1e-4, which would be the error measured here)
+    b = ref.StateVector(n, np.complex128)
+    b.set_state(a.get_state().astype(np.complex128))
     order = [int(w) for w in np.random.default_rng(n).permutation(n)]
     words, wires = ["Z"] * n + ["I"], [[w] for w in order] + [[0]]
     l0 = a.kernel_launches
     each = a.expval_pauli_words_each(words, wires)
     assert a.kernel_launches - l0 <= 2  # one sweep + the final reduction
-    tol = 10 * TOL[np.dtype(dtype)]
+    tol = 1e-12 if dtype == np.complex128 else 1e-6
     for k, w in enumerate(order):
         assert abs(each[k] - b.expval_named("PauliZ", [w])) < tol, (k, w)
-    assert abs(each[n] - 1.0) < tol
+    assert abs(each[n] - 1.0) < (1e-12 if dtype == np.complex128 else 1e-5)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -139,10 +139,16 @@ def test_long_scaled_tape_keeps_the_pending_scalar_bounded_c64(emu, plb):
     np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("specialised", [False, True])
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
-def test_adjoint_sweep_through_tile_interpreter(emu, plb, dtype):
+def test_adjoint_sweep_through_tile_interpreter(emu, plb, dtype, specialised, monkeypatch):
     """Two-state passes with in-register generator overlaps (the fused adjoint) against the oracle's
-    adjoint loop (AdjointJacobianLQubit.hpp:347-491)."""
+    adjoint loop (AdjointJacobianLQubit.hpp:347-491); `specialised`: through the generated pass code
+    (jit_codegen.hpp, compiled with g++) instead of the interpreter."""
+    if specialised:
+        monkeypatch.setenv("PLB200_EMU_JIT", "1")
+        emu.plb200_emu_jit_passes.restype = C.c_int64
+    before = emu.plb200_emu_jit_passes() if specialised else 0
     n = 13
     rng = np.random.default_rng(4)
     ops = []
@@ -177,6 +183,8 @@ def test_adjoint_sweep_through_tile_interpreter(emu, plb, dtype):
     assert rc == 0, emu.plb200_emu_last_error()
     assert stats[0] >= 1
     np.testing.assert_allclose(jac, np.asarray(expect).ravel(), rtol=0, atol=TOL[np.dtype(dtype)] * 20)
+    if specialised:
+        assert emu.plb200_emu_jit_passes() > before
 
 
 def _fuzz_tape(n, rng, m, style):

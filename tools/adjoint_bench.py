@@ -19,6 +19,9 @@ for dt, tag in ((np.complex128, "c128"), (np.complex64, "c64")):
     sv.sync()
     t0 = time.perf_counter(); e = sv.expval(ham); t_e = time.perf_counter() - t0
     t0 = time.perf_counter(); jac = sv.adjoint_jacobian([ham], ops, tp); t_j = time.perf_counter() - t0
+    jac = sv.adjoint_jacobian([ham], ops, tp)
+    plb.jit_wait()  # the two-state pass kernels are compiled from the second sighting
+    jac = sv.adjoint_jacobian([ham], ops, tp)
     t0 = time.perf_counter(); jac = sv.adjoint_jacobian([ham], ops, tp); t_j2 = time.perf_counter() - t0
     S = (1 << n) * (16 if dt == np.complex128 else 8)
     out[tag] = dict(expval=e, expval_s=t_e, adjoint_s=min(t_j, t_j2), eff_GBps=6 * S * n_params / min(t_j, t_j2) / 1e9,
