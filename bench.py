@@ -108,6 +108,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def nvlink_tx_rx_bytes(index=0):
+    """NVLink data-payload counters of one GPU (sum over its links), from `nvidia-smi nvlink -gt d`; None when the
+    tool or the counters are unavailable."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for line in out.splitlines():
+            f = line.replace(":", " ").split()
+            if "Tx" in f and "KiB" in f:
+                tx += int(f[f.index("KiB") - 1]) * 1024
+                seen = True
+            if "Rx" in f and "KiB" in f:
+                rx += int(f[f.index("KiB") - 1]) * 1024
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------ reference arm
 def time_reference(n, ops_sample, steps, warmup, threads=None):
     from oracle import lq_ref
@@ -463,6 +483,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = launches()
+    nv0 = nvlink_tx_rx_bytes(local_rank) if (world > 1 and rank == 0) else None
+    swaps0 = sv.n_swaps if world > 1 else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -471,6 +493,14 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    nvlink_measured = None
+    if world > 1 and rank == 0:
+        nv1 = nvlink_tx_rx_bytes(local_rank)
+        if nv0 and nv1:
+            dsw = max(1, sv.n_swaps - swaps0)
+            nvlink_measured = {"tx_bytes_per_step": (nv1[0] - nv0[0]) / args.steps, "rx_bytes_per_step": (nv1[1] - nv0[1]) / args.steps,
+                               "tx_bytes_per_swap": (nv1[0] - nv0[0]) / dsw, "source": "nvidia-smi nvlink -gt d, GPU of rank 0, "
+                               "difference over the timed region (includes NCCL's barrier / reduction traffic)"}
     gpu_launches = launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -661,7 +691,8 @@ def run_ours(args):
                        "index_bit_swaps_per_step": (n_swaps // max(1, args.warmup + args.steps + e2e_steps + 1))
                        if world > 1 else 0,
                        "nvlink_bytes_per_swap_per_gpu": (swap_bytes // max(1, n_swaps)) if world > 1 and
-                       n_swaps else 0},
+                       n_swaps else 0,
+                       "nvlink_counters": nvlink_measured},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tape_bytes,
                     "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "step_ms": e2e_step_ms,
