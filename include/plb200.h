@@ -268,6 +268,9 @@ int plb200_sv_ipc_handle(const plb200_sv *sv, unsigned char *handle64);
  * ping-pong slabs (every rank must synchronise before reading); 0: the tape was applied in place and the caller
  * swaps with plb200_sv_swap_bit[s]_peer.  plb200_sv_alloc_alt allocates the second slab (same size). */
 int plb200_sv_alloc_alt(plb200_sv *sv);
+/* bandwidth probe of the peer path: device-to-device copy kernel on the state's stream (either side may be a peer
+ * mapping: remote stores = push, remote loads = pull) */
+int plb200_sv_peer_copy(plb200_sv *sv, void *dst, const void *src, int64_t n_bytes, int unroll);
 void *plb200_sv_alt_ptr(const plb200_sv *sv);
 int plb200_sv_ipc_handle_alt(const plb200_sv *sv, unsigned char *handle64);
 int plb200_sv_apply_ops_route(plb200_sv *sv, const plb200_ops_t *ops, int64_t k, const int64_t *lbits,

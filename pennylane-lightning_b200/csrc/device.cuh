@@ -121,6 +121,7 @@ void set_state_on_wires(StateVec &sv, const double *vals, const std::vector<int>
 void collapse_zero(StateVec &sv, int bit, int keep_value);
 void pack_bit(const StateVec &sv, int bit, int keep, void *buf);
 void unpack_bit(StateVec &sv, int bit, int keep, const void *buf);
+void peer_copy(StateVec &sv, void *dst, const void *src, uint64_t n16, int unroll);
 void swap_bit_peer(StateVec &sv, int bit, int keep, void *peer, int do_half);
 void swap_bits_peer(StateVec &sv, const int *bits, int k, int my_value, void *const *peers);
 

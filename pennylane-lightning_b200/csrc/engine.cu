@@ -1243,6 +1243,14 @@ int plb200_sv_swap_bits_peer(plb200_sv *sv, const int64_t *bits, int64_t k, int6
     ABI_CATCH
 }
 
+// bandwidth probe (tools/peer_bw.py): copy n_bytes between device pointers on this state's stream; either pointer
+// may be a peer mapping
+int plb200_sv_peer_copy(plb200_sv *sv, void *dst, const void *src, int64_t n_bytes, int unroll) {
+    ABI_TRY
+    PLB_CHECK(n_bytes >= 0 && n_bytes % 16 == 0, "peer_copy: bytes must be a multiple of 16");
+    peer_copy(sv->s, dst, src, static_cast<uint64_t>(n_bytes / 16), unroll);
+    ABI_CATCH
+}
 int plb200_sv_ipc_handle_alt(const plb200_sv *sv, unsigned char *handle64) {
     ABI_TRY
     PLB_CHECK(sv->s.alt != nullptr, "no ping-pong slab");

@@ -493,6 +493,21 @@ __global__ void __launch_bounds__(kThreads)
     if (row < nrows && lane == 0) y[row] = mk<T2>(re, im);
 }
 
+// Bandwidth probe of the NVLink peer path (tools/peer_bw.py): dst[i] = src[i], 128-bit accesses, U in flight
+// per thread; one of the two pointers is a peer mapping (push: remote stores, pull: remote loads).
+template <int U>
+__global__ void __launch_bounds__(kThreads) peer_copy_kernel(double2 *__restrict__ dst, const double2 *__restrict__ src, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i0 = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (i0 + u * stride < n) v[u] = src[i0 + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (i0 + u * stride < n) dst[i0 + u * stride] = v[u];
+    }
+}
 BitInsert single_insert(int bit) {
     BitInsert bi;
     bi.n = 1;
@@ -968,6 +983,16 @@ void csr_apply(StateVec &out, const StateVec &in, const int64_t *d_indptr, const
     else PLB_CSR(32);
 #undef PLB_CSR
     out.launches++;
+    PLB_CUDA(cudaGetLastError());
+}
+
+void peer_copy(StateVec &sv, void *dst, const void *src, uint64_t n16, int unroll) {
+    sv.set_device();
+    const unsigned nb = static_cast<unsigned>(std::min<uint64_t>((n16 + kThreads * 4 - 1) / (kThreads * 4), uint64_t(sv.sm_count) * 32));
+    if (unroll >= 8)
+        peer_copy_kernel<8><<<nb, kThreads, 0, sv.stream>>>(static_cast<double2 *>(dst), static_cast<const double2 *>(src), n16);
+    else
+        peer_copy_kernel<4><<<nb, kThreads, 0, sv.stream>>>(static_cast<double2 *>(dst), static_cast<const double2 *>(src), n16);
     PLB_CUDA(cudaGetLastError());
 }
 
