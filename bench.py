@@ -631,16 +631,56 @@ def run_ours(args):
         n_fused_swaps = getattr(sv, "n_fused_swaps", 0)
 
     sv_ref_for_stats = _Stats
+    def make_line(extra_value):
+        return {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": f"{n}q random circuit RX/RY/RZ/CNOT/CRZ depth {DEPTH} seed {SEED}, c128, "
+                                   f"{nloc} local qubits per GPU",
+                       "qubits": n, "gates": n_gates, "fused": fuse, "hbm_passes_per_step": stats[1],
+                       "l2": "state (16 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"index-bit sharding over {world} GPU(s)",
+                       "value_definition": "ranks x gates / time: each rank applies every gate to its own "
+                                           f"2^{nloc}-amplitude slab (= plain gates/s at N=1)",
+                       "circuit_gates_per_s": n_gates * args.steps / (ms * 1e-3),
+                       "fused_index_bit_swaps_total": getattr(sv_ref_for_stats, "n_fused_swaps", 0) if world > 1 else 0,
+                       "index_bit_swaps_per_step": (n_swaps // max(1, args.warmup + args.steps + e2e_steps + 1))
+                       if world > 1 else 0,
+                       "nvlink_bytes_per_swap_per_gpu": (swap_bytes // max(1, n_swaps)) if world > 1 and
+                       n_swaps else 0,
+                       "nvlink_counters": nvlink_measured},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tape_bytes,
+                    "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "step_ms": e2e_step_ms,
+                    "what": "reset + applyOperations(host tape) + expval(PauliZ(w)) for every wire -> host"},
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "jit": plb.jit_stats(),
+            "checks": checks, "extra": extra_value,
+        }
+
     if world > 1 and os.environ.get("PLB200_BENCH_CONFIG4", "1") != "0":
         sv.close()
         del sv
         torch.cuda.empty_cache()
+        key4 = f"config4_{33 + g}q_{world}gpu"
+        limit = float(os.environ.get("PLB200_BENCH_CONFIG4_TIMEOUT", "420"))
+
+        def _watchdog():
+            # a 128-GiB-slab run that does not come back must not cost the line of the run that did
+            if rank == 0:
+                print(json.dumps(make_line({key4: {"error": f"no result within {limit:.0f} s (watchdog)"}})), flush=True)
+            os._exit(0)
+
+        timer = threading.Timer(limit, _watchdog)
+        timer.daemon = True
+        timer.start()
         try:
             c4 = config4_block(plb, circuits, DistStateVector, dist, torch, rank, world, stream)
         except Exception as exc:
             c4 = {"error": repr(exc)}
+        timer.cancel()
         if rank == 0:
-            extra = {f"config4_{33 + g}q_{world}gpu": c4}
+            extra = {key4: c4}
         sv = None
     if rank == 0 and world == 1:
         peak, _ = measured_peak()
@@ -675,32 +715,7 @@ def run_ours(args):
                 torch.cuda.empty_cache()
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"{n}q random circuit RX/RY/RZ/CNOT/CRZ depth {DEPTH} seed {SEED}, c128, "
-                                   f"{nloc} local qubits per GPU",
-                       "qubits": n, "gates": n_gates, "fused": fuse, "hbm_passes_per_step": stats[1],
-                       "l2": "state (16 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"index-bit sharding over {world} GPU(s)",
-                       "value_definition": "ranks x gates / time: each rank applies every gate to its own "
-                                           f"2^{nloc}-amplitude slab (= plain gates/s at N=1)",
-                       "circuit_gates_per_s": n_gates * args.steps / (ms * 1e-3),
-                       "fused_index_bit_swaps_total": getattr(sv_ref_for_stats, "n_fused_swaps", 0) if world > 1 else 0,
-                       "index_bit_swaps_per_step": (n_swaps // max(1, args.warmup + args.steps + e2e_steps + 1))
-                       if world > 1 else 0,
-                       "nvlink_bytes_per_swap_per_gpu": (swap_bytes // max(1, n_swaps)) if world > 1 and
-                       n_swaps else 0,
-                       "nvlink_counters": nvlink_measured},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tape_bytes,
-                    "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "step_ms": e2e_step_ms,
-                    "what": "reset + applyOperations(host tape) + expval(PauliZ(w)) for every wire -> host"},
-            "gpu_launches": int(gpu_launches), "clocks": clocks, "jit": plb.jit_stats(),
-            "checks": checks, "extra": extra,
-        }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(make_line(extra)), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

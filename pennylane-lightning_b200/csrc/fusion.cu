@@ -206,7 +206,24 @@ bool is_swap2(const COp &op) {
            b.m[1] == cd(1.0) && b.m[2] == cd(1.0);
 }
 
-FOp classify(const COp &op) {
+// Two-bit pair ops inside tile passes (K_PAIR2).  They need a specialised kernel, compiled at first sight, so
+// they are fused only when that is the regime the user chose: PLB200_JIT=sync, or PLB200_FUSE_PAIR2=1.
+bool pair2_enabled() {
+    if (const char *e = std::getenv("PLB200_FUSE_PAIR2")) return e[0] != '0';
+#if defined(PLB200_HOST_EMU)
+    return false;
+#else
+    return jit::mode() == jit::Mode::Sync && jit::available(nullptr);
+#endif
+}
+bool is_pair2(const COp &op) {
+    if (op.kind != OP_PAIRS || op.parity || op.tbits.size() != 2 || op.blocks.empty() || op.blocks.size() > 2) return false;
+    for (const Block2 &b : op.blocks)
+        if (b.a > 3 || b.b > 3 || b.a == b.b || !well_conditioned(b.m)) return false;
+    return true;
+}
+
+FOp classify(const COp &op, bool pair2 = false) {
     FOp f;
     uint64_t t = 0;
     for (int b : op.tbits) t |= uint64_t{1} << b;
@@ -217,6 +234,9 @@ FOp classify(const COp &op) {
         f.fusable = true;
         f.nd = t;
     } else if (is_swap2(op)) {
+        f.fusable = true;
+        f.nd = t;
+    } else if (pair2 && is_pair2(op)) {
         f.fusable = true;
         f.nd = t;
     } else if (op.kind == OP_DIAG) {
@@ -235,8 +255,8 @@ FOp classify(const COp &op) {
     return f;
 }
 
-FOp classify(const AdjItem &it) {
-    if (!it.overlap) return classify(it.op);
+FOp classify(const AdjItem &it, bool pair2 = false) {
+    if (!it.overlap) return classify(it.op, pair2);
     FOp f;
     const PauliWordMask &w = it.pw;
     f.nd = w.x;
@@ -318,6 +338,7 @@ struct Step {
     unsigned grid = 0;
     int nrounds = 0, nops = 0;
     bool ext = false; // needs the extended kernel (two-bit SWAPs / tail ladders)
+    bool jit_only = false; // holds K_PAIR2 ops: only a specialised kernel can run it
     std::vector<int> slots;          // adjoint: global accumulator slot of each pass-local slot
     std::vector<double> slot_scale;  // ... and the |pending scalar|^2 its overlap was taken under
 };
@@ -404,8 +425,9 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                             ((sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr);
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
     std::vector<FOp> f(items.size());
+    const bool pair2 = Cfg::NS == 1 && pair2_enabled();
     for (size_t i = 0; i < items.size(); i++) {
-        f[i] = classify(items[i]);
+        f[i] = classify(items[i], pair2);
         f[i].all &= full;
     }
     std::vector<char> done(items.size(), 0);
@@ -462,7 +484,10 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             size_t emitted = 0, keep = 0;
             for (int i : exec) {
                 const AdjItem &it = items[i];
-                emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
+                if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() == 2 && !is_swap2(it.op))
+                    emitted += 2 * it.op.blocks.size(); // K_PAIR2: one record per block (+ a pivot each at most)
+                else
+                    emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
                 if (emitted > max_pass_ops) break;
                 keep++;
             }
@@ -657,6 +682,28 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 } else if (is_swap2(it.op)) {
                     st.ext = true;
                     t.code = make_code(cm_reg ? K_SWAP2_M : K_SWAP2, reg_pos(it.op.tbits[0]), reg_pos(it.op.tbits[1]));
+                } else if (it.op.kind == OP_PAIRS && it.op.tbits.size() == 2) {
+                    // two-bit pair op: one K_PAIR2 record per 2x2 block (a pivot X on the pair first when needed)
+                    st.jit_only = true;
+                    const int p = reg_pos(it.op.tbits[0]), c = reg_pos(it.op.tbits[1]);
+                    t.code = make_code(K_PAIR2, p, c);
+                    if (t.cm_tid | t.cmask_o) t.code |= F_COND;
+                    for (const Block2 &bl : it.op.blocks) {
+                        const PairForm pf = pair_form(bl.m, false);
+                        TileOp<T2> rec = t;
+                        if (pf.pre_swap) {
+                            TileOp<T2> x = t;
+                            x.slot = bl.a | (bl.b << 2) | (static_cast<uint32_t>(K_SWAP) << 4);
+                            top[op_cursor++] = x;
+                        }
+                        rec.slot = bl.a | (bl.b << 2) | (static_cast<uint32_t>(pf.kind) << 4);
+                        for (int q = 0; q < 4; q++) rec.m[q] = mk<T2>(pf.m[q].real(), pf.m[q].imag());
+#if defined(PLB200_HOST_EMU)
+                        g_kind_hist[K_PAIR2]++;
+#endif
+                        top[op_cursor++] = rec;
+                    }
+                    return;
                 } else if (it.op.kind == OP_PAIRS) {
                     const int p = reg_pos(it.op.tbits[0]);
                     const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0);
@@ -902,8 +949,10 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         else {
             // the pass's specialised kernel when the cache has it (jit_runtime.cpp), else the interpreter
             jit::Kernel k;
-            if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>());
+            if (use_jit || st.jit_only)
+                k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>(), st.jit_only);
             if (k) jit::launch(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream, sv.data, pp);
+            else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
             else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
@@ -943,8 +992,9 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
     bool have = false;
     auto launch_plain = [&](const Step &st, const PassParams<T2> &pp) {
         jit::Kernel k;
-        if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem);
+        if (use_jit || st.jit_only) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem, st.jit_only);
         if (k) jit::launch(k, st.grid, nt, smem, sv.stream, sv.data, &pp);
+        else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
         else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, pp);
         sv.launches++;
     };
@@ -1148,8 +1198,9 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
             return;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if (std::getenv("PLB200_EMU_JIT") && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
-        } else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
+        if ((st.jit_only || std::getenv("PLB200_EMU_JIT")) && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
+        } else if (st.jit_only) fail("emu: a pass with two-bit pair ops has no specialised source");
+        else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
         else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
@@ -1168,6 +1219,7 @@ int emulate_routed_typed(int n, const std::vector<AdjItem> &items, bool scaled, 
     auto plain = [&](const Step &st, const PassParams<T2> &pp) {
         std::vector<double> acc(kMaxPassOps, 0.0);
         if (emulate_pass_jit<T2, Cfg>(sv0, pp)) return;
+        if (st.jit_only) fail("emu: a pass with two-bit pair ops has no specialised source");
         if (st.ext) emulate_pass<T2, Cfg, true>(sv0, nullptr, acc.data(), pp);
         else emulate_pass<T2, Cfg, false>(sv0, nullptr, acc.data(), pp);
     };

@@ -576,6 +576,43 @@ template <typename T2, class Cfg> class Gen {
                 close_cond();
             }
         } break;
+        case K_PAIR2: { // one 2x2 block of a two-bit pair op on the registers with (C, P) = a and = b
+            const unsigned a2 = op.slot & 3u, b2 = (op.slot >> 2) & 3u;
+            const int form = static_cast<int>((op.slot >> 4) & 15u);
+            auto dep = [&](unsigned x) { return static_cast<int>(((x & 1u) << P) | ((x >> 1) << C)); };
+            pr.clear();
+            for (int u = 0; u < NV; u++) {
+                if (((u >> P) & 1) || ((u >> C) & 1)) continue;
+                const int ua = u | dep(a2), ub = u | dep(b2);
+                if (!((op.umask >> ua) & 1u)) continue;
+                pr.emplace_back(ua, ub);
+            }
+            if (form == K_SWAP) {
+                if (cond.empty()) {
+                    if (last)
+                        for (auto [x, y] : pr) std::swap(perm[x], perm[y]);
+                    s += "        // register renaming\n";
+                } else {
+                    open_cond();
+                    for (auto [x, y] : pr) add("            cswap(%s, %s);\n", V(x).c_str(), V(y).c_str());
+                    close_cond();
+                }
+                break;
+            }
+            decl_m(form == K_LU_C ? 4 : form == K_LU_R ? 2 : 1);
+            open_cond();
+            for (auto [x, y] : pr) {
+                const std::string va = V(x), vb = V(y);
+                switch (form) {
+                case K_LIFT_R: add("            lift_r(%s, %s, m0);\n", va.c_str(), vb.c_str()); break;
+                case K_LIFT_I: add("            lift_i(%s, %s, m0);\n", va.c_str(), vb.c_str()); break;
+                case K_LU_R: add("            lu_r(%s, %s, m0, m1);\n", va.c_str(), vb.c_str()); break;
+                case K_LU_C: add("            lu_c(%s, %s, m0, m1, m2, m3);\n", va.c_str(), vb.c_str()); break;
+                default: ok = false; break;
+                }
+            }
+            close_cond();
+        } break;
         case K_DIAG_R: case K_DIAG_PP: case K_DIAG_CR: {
             decl_dab();
             open_cond();

@@ -124,6 +124,13 @@ enum : int {
     K_OVL_X = 23,
     K_OVL_Y = 24,
     K_OVL_D = 25, // G = diag(g[parity]), g = (m[0].x, m[0].y)
+    // One 2x2 block of a TWO-bit pair op (IsingXX / XY / YY, SingleExcitation(+-), PSWAP, ...): register bits P, C
+    // carry the op's two target bits; the block acts on the amplitudes with (C, P) = a and = b (2-bit values in
+    // slot bits 0-1 / 2-3), in the in-place form slot bits 4-7 (K_LIFT_R / K_LIFT_I / K_LU_R / K_LU_C / K_SWAP),
+    // for the registers with umask set.  Only the SPECIALISED kernels implement it (jit_codegen.hpp): a pass
+    // holding one is never handed to the interpreter.
+    K_PAIR2 = 26,
+    K_LAST_OVL = K_OVL_D,
     K_FIRST_DIAG = K_DIAG_R,
     K_FIRST_OVL = K_OVL_X,
 };
@@ -135,7 +142,7 @@ constexpr uint32_t F_OVL = 1u << 22;  // adjoint overlap op
 PLB_HD constexpr int kind_cases(int kind) {
     return (kind == K_DIAG_PP || kind == K_SWAP_CR || kind == K_DIAG_CR || kind == K_SWAP2 || kind == K_SWAP2_M)
                ? kMaxR * (kMaxR - 1)
-           : (kind == K_LADDER)                                            ? 0
+           : (kind == K_LADDER || kind == K_PAIR2)                         ? 0
            : (kind == K_DIAG_T || kind == K_DIAG1_T || kind == K_DIAG_G) ? 1
                                                                         : kMaxR;
 }
@@ -149,7 +156,7 @@ PLB_HD constexpr uint32_t make_code(int kind, int p, int c) {
     const int n = kind_cases(kind);
     const int sub = n == kMaxR * (kMaxR - 1) ? pc_index(p, c) : n == kMaxR ? p : 0;
     return static_cast<uint32_t>(kind_base(kind) + sub) | static_cast<uint32_t>(kind) << 8 |
-           static_cast<uint32_t>(p) << 13 | static_cast<uint32_t>(c) << 16 | (kind >= K_FIRST_OVL ? F_OVL : 0u);
+           static_cast<uint32_t>(p) << 13 | static_cast<uint32_t>(c) << 16 | ((kind >= K_FIRST_OVL && kind <= K_LAST_OVL) ? F_OVL : 0u);
 }
 PLB_HD constexpr int code_kind(uint32_t code) { return static_cast<int>((code >> 8) & 31u); }
 PLB_HD constexpr int code_p(uint32_t code) { return static_cast<int>((code >> 13) & 7u); }

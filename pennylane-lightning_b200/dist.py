@@ -404,12 +404,13 @@ class DistStateVector:
         partner = self.rank ^ (1 << r)
         keep = (self.rank >> r) & 1  # this rank keeps local bit == its rank bit
         if self.swap_mode == "peer":
-            # both partners exchange half of the pair range each, in place, with 128-bit peer loads/stores
-            self.engine.sync()
-            dist.barrier(group=self.group)
+            # both partners exchange half of the pair range each, in place, with 128-bit peer loads/stores.
+            # Device-side fences instead of host barriers: a stream-ordered all_reduce completes only when every
+            # rank has finished what precedes it, so the partner's slab is quiescent before the exchange touches it
+            # and complete before the next pass reads it — and the host keeps scheduling ahead
+            self._fence_all()
             self.engine.swap_bit_peer(lb, keep, partner, 1 + keep)
-            self.engine.sync()
-            dist.barrier(group=self.group)
+            self._fence_all()
             self.phys[gw], self.phys[lw] = lb, gb
             self.n_swaps += 1
             self.swap_bytes += (1 << (self.nloc - 1)) * self.dtype.itemsize
@@ -424,6 +425,16 @@ class DistStateVector:
         self.phys[gw], self.phys[lw] = lb, gb
         self.n_swaps += 1
         self.swap_bytes += send.numel() * send.element_size()
+
+    def _fence_all(self):
+        """Stream-ordered barrier over the ranks (no host synchronisation)."""
+        if self.dist.get_backend(self.group) != "nccl":
+            self.engine.sync()
+            self.dist.barrier(group=self.group)
+            return
+        if not hasattr(self, "_fence"):
+            self._fence = self.torch.zeros(1, device="cuda")
+        self.dist.all_reduce(self._fence, group=self.group)
 
     def _swap_multi(self, pairs):
         """Exchange several (global wire, local wire) pairs in ONE all-to-all over peer memory:
@@ -440,11 +451,9 @@ class DistStateVector:
                 bit = 1 << (gb - self.nloc)
                 r = (r | bit) if (p >> i) & 1 else (r & ~bit)
             partner_ranks.append(r)
-        self.engine.sync()
-        dist.barrier(group=self.group)
+        self._fence_all()
         self.engine.swap_bits_peer(lbits, my_value, partner_ranks)
-        self.engine.sync()
-        dist.barrier(group=self.group)
+        self._fence_all()
         for (gw, lw), gb, lb in zip(pairs, gbits, lbits):
             self.phys[gw], self.phys[lw] = lb, gb
         self.n_swaps += k
@@ -549,9 +558,7 @@ class DistStateVector:
         # it — so every peer's stores into this rank's ping-pong slab have landed before anything reads it, while
         # the host runs ahead and schedules the next segment (a host sync here idles the GPU for the ~10 ms of
         # Python that classify the rest of the tape: measured 8 ms per exchange at N = 8)
-        if not hasattr(self, "_fence"):
-            self._fence = self.torch.zeros(1, device="cuda")
-        dist.all_reduce(self._fence, group=self.group)
+        self._fence_all()
         self.engine.flip_slabs()
         for (gw, lw), gb, lb in zip(pairs, gbits, lbits):
             self.phys[gw], self.phys[lw] = lb, gb

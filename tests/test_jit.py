@@ -85,6 +85,56 @@ def test_generated_code_on_host_matches_oracle(plb, dtype, monkeypatch):
     assert emu.plb200_emu_jit_passes() > before
 
 
+def _pair2_tape(n, seed, count=120):
+    """Rotations + the two-qubit gates whose action is 2x2 blocks on amplitude pairs of a 4-dimensional subspace."""
+    rng = np.random.default_rng(seed)
+    names2 = ["IsingXX", "IsingXY", "IsingYY", "SingleExcitation", "SingleExcitationPlus", "SingleExcitationMinus", "PSWAP",
+              "CNOT", "IsingZZ"]
+    ops = []
+    for _ in range(count):
+        if rng.random() < 0.45:
+            ops.append(circuits.op(("RX", "RY", "RZ", "Hadamard")[int(rng.integers(4))], [int(rng.integers(n))],
+                                   [rng.uniform(0, 6)] if rng.random() < 2 else []))
+            if ops[-1]["name"] == "Hadamard":
+                ops[-1]["params"] = []
+        else:
+            nm = names2[int(rng.integers(len(names2)))]
+            w = [int(x) for x in rng.permutation(n)[:4]]
+            ctrl = w[2:3] if (rng.random() < 0.25 and nm not in ("CNOT",)) else []
+            ops.append(circuits.op(nm, w[:2], [rng.uniform(0, 6)] if nm != "CNOT" else [], inverse=bool(rng.integers(2)),
+                                   ctrl_wires=ctrl, ctrl_values=[bool(rng.integers(2))] * len(ctrl)))
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_two_bit_pair_ops_fused_on_host(plb, dtype, monkeypatch):
+    """PLB200_FUSE_PAIR2=1: IsingXX / XY / YY, SingleExcitation(+-), PSWAP (also controlled) run INSIDE the tile
+    passes as K_PAIR2 ops of the generated code: no stand-alone kernels, oracle's amplitudes."""
+    import subprocess
+
+    from test_tile_emulation import CSRC, EMU, emu_apply, oracle_apply
+
+    res = subprocess.run(["make", "-C", CSRC, "-j8", "emu"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    emu = C.CDLL(EMU)
+    emu.plb200_emu_last_error.restype = C.c_char_p
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "1")
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 14
+    ops = _pair2_tape(n, 3)
+    st = random_state(n, dtype, 9)
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    assert stats[1] == 0, stats  # nothing ran stand-alone
+    np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=TOL[np.dtype(dtype)])
+    hist = (C.c_int64 * 32)()
+    emu.plb200_emu_kind_histogram(hist, 1)
+    assert hist[26] > 0  # K_PAIR2 records were emitted
+    # without the switch the same tape leaves those gates stand-alone
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "0")
+    _, stats0 = emu_apply(emu, plb, n, ops, st, True)
+    assert stats0[1] > 0
+
+
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.fixture
 def jit_sync(plb, monkeypatch):
@@ -192,3 +242,23 @@ def test_jit_adjoint_passes_match_reference(plb, ref, jit_sync, dtype):
     ji = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
     plb.jit_set_mode(2)
     np.testing.assert_allclose(ja, ji, rtol=0, atol=1e-11 if dtype == np.complex128 else 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_jit_two_bit_pair_ops_fused(plb, ref, jit_sync, dtype):
+    """In the compile-at-first-sight regime the two-bit pair gates are tile ops: one launch per pass, no stand-alone
+    kernels in between, reference amplitudes."""
+    n = 17
+    ops = _pair2_tape(n, 4, 200)
+    st = random_state(n, dtype, 5)
+    a, r = plb.StateVector(n, dtype), ref.StateVector(n, dtype)
+    a.set_state(st), r.set_state(st)
+    blob = plb.OpsBlob(ops)
+    stats = (C.c_int64 * 4)()
+    assert plb.lib().plb200_schedule_stats(C.c_int64(n), 64 if dtype == np.complex128 else 32, blob.ptr(), stats) == 0
+    assert stats[1] == 0 and stats[0] >= 1, list(stats)
+    a.apply_ops(blob, fuse=True)
+    r.apply_ops(ops)
+    assert a.last_apply_stats()[1] == stats[0]
+    np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=TOL[np.dtype(dtype)])
