@@ -339,6 +339,8 @@ struct Step {
     int nrounds = 0, nops = 0;
     bool ext = false; // needs the extended kernel (two-bit SWAPs / tail ladders)
     bool jit_only = false; // holds K_PAIR2 ops: only a specialised kernel can run it
+    bool jit_forms = false; // encoded with forms only the specialised kernels have (scaled rotations, in-stream
+                            // ladders); a consumer that cannot run it says so and gets the interpreter encoding
     std::vector<int> slots;          // adjoint: global accumulator slot of each pass-local slot
     std::vector<double> slot_scale;  // ... and the |pending scalar|^2 its overlap was taken under
 };
@@ -354,7 +356,10 @@ struct PairForm {
 inline bool is_real(cd z) { return z.imag() == 0.0; }
 inline bool is_imag(cd z) { return z.real() == 0.0; }
 
-PairForm pair_form(const cd *min, bool fold) {
+// jf ("jit forms", only together with fold): the pass will run as a specialised kernel, which has the scaled
+// rotations K_SRO[TK]_[RI] (4 FMAs per pair; the cosine or sine goes to the host-carried scalar).  max_growth:
+// largest 1 / |cos| the tangent form may take (the stored amplitudes grow by it).
+PairForm pair_form(const cd *min, bool fold, bool jf = false, double max_growth = 1.0) {
     PairForm f;
     cd m[4] = {min[0], min[1], min[2], min[3]};
     if (m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0)) {
@@ -363,6 +368,19 @@ PairForm pair_form(const cd *min, bool fold) {
     }
     const bool all_real = is_real(m[0]) && is_real(m[1]) && is_real(m[2]) && is_real(m[3]);
     const bool rx_like = is_real(m[0]) && is_real(m[3]) && is_imag(m[1]) && is_imag(m[2]);
+    if (fold && jf) {
+        // [[c, -s], [s, c]] = c [[1, -t], [t, 1]] = s [[k, -1], [1, k]];  [[c, -is], [-is, c]] likewise with -i s
+        const bool ry = all_real && m[0] == m[3] && m[1] == -m[2];
+        const bool rx = rx_like && m[0] == m[3] && m[1] == m[2];
+        if (ry || rx) {
+            const double c = m[0].real(), sn = ry ? m[2].real() : -m[2].imag();
+            if (std::abs(c * c + sn * sn - 1.0) <= 8e-16) {
+                if (std::abs(c) * max_growth >= 1.0) f.kind = ry ? K_SROT_R : K_SROT_I, f.m[0] = cd(sn / c, 0.0), f.s = c;
+                else f.kind = ry ? K_SROK_R : K_SROK_I, f.m[0] = cd(c / sn, 0.0), f.s = ry ? cd(sn) : cd(0.0, -sn);
+                return f;
+            }
+        }
+    }
     // rotations [[c, -s], [s, c]] / [[c, -is], [-is, c]] with c^2 + s^2 = 1: three shears
     //   [[1, u], [0, 1]] [[1, 0], [l, 1]] [[1, u], [0, 1]],  l = s, u = -s / (1 + c)   (c >= 0)
     // (c < 0: rotate by the angle - pi instead and carry the sign, if a global scalar may be carried)
@@ -405,8 +423,14 @@ PairForm pair_form(const cd *min, bool fold) {
 //
 // Steps are handed to on_step(step, pass description or nullptr) AS THEY ARE PRODUCED, so the caller can
 // launch pass k while pass k+1 is being scheduled (the description is reused: consume it in the call).
+//
+// jit_forms: tile passes are first encoded with the forms of the specialised kernels (pair_form's scaled
+// rotations; controlled phases sharing a register bit merged into in-stream ladders).  on_step may return
+// bool for a tile pass: false = "cannot run this encoding" (no kernel yet in the asynchronous tier), and the
+// pass is encoded again in the interpreter's forms and handed over a second time.  The schedule itself (tiles,
+// rounds, order) is the same either way; only the records and the host-carried scalar differ.
 template <typename T2, class Cfg, class OnStep>
-void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled, OnStep &&on_step) {
+void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled, bool jit_forms, OnStep &&on_step) {
     constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NTB = M - R, SB = Swz<T2>::B;
     constexpr bool is_double = sizeof(T2) == 16;
     constexpr size_t kMinLadder = 6; // shorter runs are cheaper as ordinary ops in the lean kernel
@@ -486,6 +510,8 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 const AdjItem &it = items[i];
                 if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() == 2 && !is_swap2(it.op))
                     emitted += 2 * it.op.blocks.size(); // K_PAIR2: one record per block (+ a pivot each at most)
+                else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG)
+                    emitted += 2; // a controlled two-valued diagonal may split into two controlled phases
                 else
                     emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
                 if (emitted > max_pass_ops) break;
@@ -525,7 +551,8 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         bool tape_done = true;
         for (size_t i = first; i < items.size() && tape_done; i++) tape_done = done[i] != 0;
 
-        // ---- encode the plan
+        // ---- encode the plan (jf: in the forms of the specialised kernels)
+        auto encode = [&](const bool jf) -> Step {
         std::memset(static_cast<void *>(cur.get()), 0, sizeof(PassParams<T2>));
         PassHdr *hdr = &cur->hdr;
         RoundHdr *rh = cur->rounds;
@@ -613,6 +640,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     if (local_mask >> tpos[i] & 1) m |= 1u << i;
                 return m;
             };
+            double round_growth = 1.0; // growth of the stored amplitudes by this round's scaled rotations
             auto reg_of_local = [&](int lp) { return static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin()); };
             auto reg_pos = [&](int global_bit) { return reg_of_local(local_of[global_bit]); };
             auto roff_of = [&](int u) {
@@ -622,7 +650,9 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 return o;
             };
 
-            auto emit_item = [&](int idx) {
+            // phase_S / phase: instead of the item itself, emit "multiply by `phase` where every bit of phase_S
+            // is 1" (one factor of a diagonal item that was parked as controlled phases)
+            auto emit_item = [&](int idx, uint64_t phase_S = 0, cd phase = cd(1.0)) {
                 const AdjItem &it = items[idx];
                 const FOp &fo = f[idx];
                 TileOp<T2> t;
@@ -631,6 +661,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 uint64_t cval = it.overlap ? it.pw.cval : it.op.cval;
                 uint64_t pmask = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : fo.pmask);
                 cd d0 = fo.d[0], d1 = fo.d[1];
+                if (phase_S) cmask = cval = phase_S, pmask = 0, d0 = d1 = phase;
                 const bool is_diag = !it.overlap && it.op.kind != OP_PAIRS;
                 if (is_diag) {
                     if (pmask == 0) { // one scalar d0 == d1 on the control subspace
@@ -706,7 +737,11 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     return;
                 } else if (it.op.kind == OP_PAIRS) {
                     const int p = reg_pos(it.op.tbits[0]);
-                    const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0);
+                    // tangent-form rotations let the stored amplitudes grow by 1 / |cos|: at most 2^16 per
+                    // rotation and 2^40 (c64) / 2^400 (c128) per round on top of the carried scalar's own range
+                    const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0, jf,
+                                                  std::min(0x1p16, (is_double ? 0x1p400 : 0x1p40) / round_growth));
+                    if (pf.kind >= K_SROT_R && pf.kind <= K_SROK_I) st.jit_forms = true, round_growth /= std::abs(pf.s);
                     const bool masked = cm_reg != 0;
                     auto masked_kind = [](int k) {
                         return k == K_LIFT_R ? K_LIFT_R_M : k == K_LIFT_I ? K_LIFT_I_M : k == K_LU_R ? K_LU_R_M
@@ -769,31 +804,79 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 uint64_t S;
                 cd phase, fold;
             };
-            auto ladder_entry = [&](int idx, LEntry &e) {
+            // factors of a diagonal item as controlled phases (0: the item is emitted as an ordinary op)
+            auto ladder_entries = [&](int idx, LEntry (&e)[2]) {
                 const AdjItem &it = items[idx];
                 const FOp &fo = f[idx];
-                if (it.overlap || it.op.kind != OP_DIAG) return false;
-                e.idx = idx, e.fold = cd(1.0);
+                if (it.overlap || it.op.kind != OP_DIAG) return 0;
+                int ne = 0;
                 if (fo.pmask == 0) {
-                    if (it.op.cmask == 0 || it.op.cval != it.op.cmask) return false;
-                    e.S = it.op.cmask, e.phase = fo.d[0];
-                } else {
-                    if (__builtin_popcountll(fo.pmask) != 1 || it.op.cmask != 0 || !allow_scaled) return false;
-                    e.S = fo.pmask, e.fold = fo.d[0], e.phase = fo.d[1] / fo.d[0];
-                }
-                return __builtin_popcount(to_local(e.S & T) & rmask_l) <= 1;
+                    if (it.op.cmask == 0 || it.op.cval != it.op.cmask) return 0;
+                    e[ne++] = LEntry{idx, it.op.cmask, fo.d[0], cd(1.0)};
+                } else if (__builtin_popcountll(fo.pmask) == 1 && it.op.cmask == 0) {
+                    if (!allow_scaled) return 0;
+                    e[ne++] = LEntry{idx, fo.pmask, fo.d[1] / fo.d[0], fo.d[0]};
+                } else if (jf && __builtin_popcountll(fo.pmask) == 1 && it.op.cval == it.op.cmask) {
+                    // controlled diag(d0, d1) (CRZ ...): d0 on the control subspace, d1 / d0 where the target is set too
+                    if (fo.d[0] != cd(1.0)) e[ne++] = LEntry{idx, it.op.cmask, fo.d[0], cd(1.0)};
+                    e[ne++] = LEntry{idx, it.op.cmask | fo.pmask, fo.d[1] / fo.d[0], cd(1.0)};
+                } else
+                    return 0;
+                for (int q = 0; q < ne; q++)
+                    if (__builtin_popcount(to_local(e[q].S & T) & rmask_l) > 1) return 0;
+                return ne;
             };
             std::vector<LEntry> bucket[kMaxR + 1];
+            // header + packed entries of one ladder on register bit bk (bk = R: none) at the cursor
+            auto emit_ladder = [&](int bk) {
+                TileOp<T2> hd;
+                std::memset(&hd, 0, sizeof(hd));
+                hd.code = make_code(K_LADDER, bk, 0);
+                hd.slot = static_cast<uint32_t>(bucket[bk].size());
+#if defined(PLB200_HOST_EMU)
+                g_kind_hist[K_LADDER]++;
+#endif
+                const int nrec = ladder_records<T2>(static_cast<int>(bucket[bk].size()));
+                if (op_cursor + nrec > kMaxPassOps) fail("fusion: pass description overflow");
+                top[op_cursor] = hd;
+                std::memset(static_cast<void *>(top + op_cursor + 1), 0, sizeof(TileOp<T2>) * static_cast<size_t>(nrec - 1));
+                LadderEntry<T2> *ens = reinterpret_cast<LadderEntry<T2> *>(top + op_cursor + 1);
+                for (const LEntry &e : bucket[bk]) {
+                    ens->cmask_o = e.S & ~T;
+                    ens->cm_tid = to_tid(to_local(e.S & T) & ~rmask_l);
+                    ens->ph = mk<T2>(e.phase.real(), e.phase.imag());
+                    ens++;
+                    sigma *= e.fold;
+                }
+                op_cursor += nrec;
+                bucket[bk].clear();
+            };
+            // parked phases of bucket bk as ops at the cursor: the interpreter's forms emit the items themselves;
+            // the specialised kernels take two or more as ONE in-stream ladder (one scalar per thread, one multiply)
             auto flush_bucket = [&](int bk) {
-                for (const LEntry &e : bucket[bk]) emit_item(e.idx);
+                if (bucket[bk].empty()) return;
+                if (jf && bucket[bk].size() >= 2) {
+                    st.jit_forms = true;
+                    emit_ladder(bk);
+                    return;
+                }
+                for (const LEntry &e : bucket[bk]) {
+                    if (jf) {
+                        sigma *= e.fold;
+                        if (e.S != 0) emit_item(e.idx, e.S, e.phase);
+                    } else
+                        emit_item(e.idx);
+                }
                 bucket[bk].clear();
             };
             for (int idx : hp.rounds[r]) {
                 const AdjItem &it = items[idx];
-                LEntry e;
-                if (ladder_entry(idx, e)) {
-                    const uint32_t sreg = to_local(e.S & T) & rmask_l;
-                    bucket[sreg ? reg_of_local(__builtin_ctz(sreg)) : R].push_back(e);
+                LEntry e[2];
+                if (const int ne = ladder_entries(idx, e)) {
+                    for (int q = 0; q < ne; q++) {
+                        const uint32_t sreg = to_local(e[q].S & T) & rmask_l;
+                        bucket[sreg ? reg_of_local(__builtin_ctz(sreg)) : R].push_back(e[q]);
+                    }
                     continue;
                 }
                 // non-diagonal action on register bits: parked phases on those bits must come first
@@ -806,7 +889,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 emit_item(idx);
             }
             for (int bk = 0; bk <= R; bk++)
-                if (bucket[bk].size() < kMinLadder) flush_bucket(bk);
+                if (jf || bucket[bk].size() < kMinLadder) flush_bucket(bk);
             const bool last_round = r + 1 == hp.rounds.size();
             const double mag = std::abs(sigma);
             if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && (Cfg::NS == 2 || tape_done)))) {
@@ -817,26 +900,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             for (int bk = 0; bk <= R; bk++) {
                 if (bucket[bk].empty()) continue;
                 st.ext = true;
-                TileOp<T2> hd;
-                std::memset(&hd, 0, sizeof(hd));
-                hd.code = make_code(K_LADDER, bk, 0);
-                hd.slot = static_cast<uint32_t>(bucket[bk].size());
-#if defined(PLB200_HOST_EMU)
-                g_kind_hist[K_LADDER]++;
-#endif
-                top[op_cursor] = hd;
-                const int nrec = ladder_records<T2>(static_cast<int>(bucket[bk].size()));
-                if (op_cursor + nrec > kMaxPassOps) fail("fusion: pass description overflow");
-                std::memset(static_cast<void *>(top + op_cursor + 1), 0, sizeof(TileOp<T2>) * static_cast<size_t>(nrec - 1));
-                LadderEntry<T2> *ens = reinterpret_cast<LadderEntry<T2> *>(top + op_cursor + 1);
-                for (const LEntry &e : bucket[bk]) {
-                    ens->cmask_o = e.S & ~T;
-                    ens->cm_tid = to_tid(to_local(e.S & T) & ~rmask_l);
-                    ens->ph = mk<T2>(e.phase.real(), e.phase.imag());
-                    ens++;
-                    sigma *= e.fold;
-                }
-                op_cursor += nrec;
+                emit_ladder(bk);
             }
             rh[r].nlad = op_cursor - rh[r].first_op - rh[r].nops;
             if (op_cursor > kMaxPassOps) fail("fusion: pass description overflow");
@@ -845,7 +909,23 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         hdr->nslots = static_cast<int>(st.slots.size());
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
         st.nrounds = hdr->nrounds, st.nops = static_cast<int>(pass_ops.size());
-        on_step(st, cur.get());
+        return st;
+        }; // encode
+        auto deliver = [&](const Step &st) {
+            if constexpr (std::is_same_v<decltype(on_step(st, cur.get())), bool>) return on_step(st, cur.get());
+            else {
+                on_step(st, cur.get());
+                return true;
+            }
+        };
+        const cd sigma_in = sigma;
+        Step st = encode(jit_forms);
+        if (!deliver(st)) {
+            if (!st.jit_forms) fail("fusion: a pass in the interpreter's forms was refused");
+            sigma = sigma_in;
+            st = encode(false);
+            if (!deliver(st)) fail("fusion: a pass in the interpreter's forms was refused");
+        }
     }
     if (sigma != cd(1.0)) {
         // stand-alone ops followed the last pass: the carried scalar needs a sweep of its own
@@ -905,6 +985,11 @@ bool scaled_forms_enabled() {
     const char *e = std::getenv("PLB200_FUSE_SCALED");
     return !(e && e[0] == '0');
 }
+// encode passes in the forms of the specialised kernels first (PLB200_JIT_FORMS=0: the interpreter's forms only)
+bool jit_forms_enabled() {
+    const char *e = std::getenv("PLB200_JIT_FORMS");
+    return !(e && e[0] == '0');
+}
 
 // Opt the kernels into their dynamic shared memory size, once per device (the attribute is per device:
 // DevicePool / batched adjoint runs drive several GPUs from one process).
@@ -941,18 +1026,21 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         PLB_CUDA(cudaEventCreate(&ev0));
         PLB_CUDA(cudaEventCreate(&ev1));
     }
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(),
-                            [&](const Step &st, const PassParams<T2> *pp) {
+    bool refused = false; // the pass at hand came back in the interpreter's forms: its kernel is not there yet
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
         if (st.op >= 0) launch_op(sv, ops[st.op]);
         else if (st.op == -2) scale(sv, st.scale);
         else {
             // the pass's specialised kernel when the cache has it (jit_runtime.cpp), else the interpreter
             jit::Kernel k;
-            if (use_jit || st.jit_only)
+            if ((use_jit && !refused) || st.jit_only)
                 k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>(), st.jit_only);
+            refused = false;
             if (k) jit::launch(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream, sv.data, pp);
             else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
+            else if (st.jit_forms) return !(refused = true);
             else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
@@ -970,6 +1058,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
                 std::fprintf(stderr, ": %.3f ms\n", ms);
             }
         }
+        return true;
     });
     if (trace) {
         cudaEventDestroy(ev0);
@@ -990,23 +1079,33 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
     auto held = std::make_unique<PassParams<T2>>();
     Step held_st;
     bool have = false;
+    bool held_interp = false; // the held pass is the interpreter's encoding of a refused pass: no kernel to look for
     auto launch_plain = [&](const Step &st, const PassParams<T2> &pp) {
         jit::Kernel k;
-        if (use_jit || st.jit_only) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem, st.jit_only);
+        if ((use_jit && !held_interp) || st.jit_only)
+            k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem, st.jit_only || st.jit_forms);
         if (k) jit::launch(k, st.grid, nt, smem, sv.stream, sv.data, &pp);
         else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
         else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, pp);
         sv.launches++;
     };
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(),
-                            [&](const Step &st, const PassParams<T2> *pp) {
+    bool refused = false;
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (have) launch_plain(held_st, *held), have = false; // the held pass was not the last step
         if (st.op >= 0) launch_op(sv, ops[st.op]);
         else if (st.op == -2) scale(sv, st.scale);
         else {
+            // A pass in the specialised forms is held only when its plain kernel exists already (it may turn
+            // out not to be the last one); otherwise it comes back in the interpreter's forms.
+            if (st.jit_forms && jit::mode() != jit::Mode::Sync &&
+                !jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem, false))
+                return !(refused = true);
             std::memcpy(static_cast<void *>(held.get()), pp, sizeof(PassParams<T2>));
-            held_st = st, have = true;
+            held_st = st, have = true, held_interp = refused;
+            refused = false;
         }
+        return true;
     });
     if (!have) {
         // the schedule did not end with a tile pass (stand-alone kernels at the end, or a tiny batch): an op-less
@@ -1040,8 +1139,9 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         std::vector<double> scale;
     };
     std::vector<PassSlots> passes;
-    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(),
-                            [&](const Step &st, const PassParams<T2> *pp) {
+    bool refused = false;
+    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+                            [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (st.op >= 0) {
             const AdjItem &it = items[st.op];
             if (it.overlap) {
@@ -1053,12 +1153,14 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
                 launch_op(hl, it.op);
             }
             stats[1]++;
-            return;
+            return true;
         }
         if (st.op == -2) fail("fusion: adjoint passes carry no scalar across passes");
         double *pacc = dacc + passes.size() * kMaxPassOps;
         jit::Kernel k;
-        if (use_jit) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
+        if (use_jit && !refused) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
+        refused = false;
+        if (!k && st.jit_forms) return !(refused = true);
         if (k) {
             void *a0 = lambda.data, *a1 = hl.data;
             void *args[4] = {&a0, &a1, &pacc, const_cast<PassParams<T2> *>(pp)};
@@ -1069,6 +1171,7 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         passes.push_back({st.slots, st.slot_scale});
         stats[0]++;
         stats[2] += st.nops;
+        return true;
     });
     if (!passes.empty()) {
         std::vector<double> h(passes.size() * kMaxPassOps);
@@ -1091,20 +1194,22 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
         if (s.op >= 0) out[1]++;
         else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
     };
-    if (precision == 64) build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, count);
-    else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, count);
+    if (precision == 64) build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, false, count);
+    else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, false, count);
 }
 
 // Host-only: the specialised source of every tile pass of the tape (tools, tests, compile-time checks).
 void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector<std::string> &out) {
     const auto items = as_items(ops);
+    const char *jfe = std::getenv("PLB200_JIT_FORMS");
+    const bool jit_forms = !(jfe && jfe[0] == '0'); // what the specialised tier compiles
     out.clear();
     if (precision == 64)
-        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, [&](const Step &s, const PassParams<double2> *pp) {
+        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<double2> *pp) {
             if (s.op == -1) out.push_back(jit::generate_pass_source<double2, FwdCfg<double2>>(*pp));
         });
     else
-        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, [&](const Step &s, const PassParams<float2> *pp) {
+        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<float2> *pp) {
             if (s.op == -1) out.push_back(jit::generate_pass_source<float2, FwdCfg<float2>>(*pp));
         });
 }
@@ -1180,7 +1285,9 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
     int rc = 0;
-    build_schedule<T2, Cfg>(n, 148, items, scaled, [&](const Step &st, const PassParams<T2> *pp) {
+    const char *jfe = std::getenv("PLB200_JIT_FORMS");
+    const bool jit_forms = std::getenv("PLB200_EMU_JIT") != nullptr && !(jfe && jfe[0] == '0');
+    build_schedule<T2, Cfg>(n, 148, items, scaled, jit_forms, [&](const Step &st, const PassParams<T2> *pp) {
         if (rc) return;
         if (st.op >= 0) {
             stats[1]++;
@@ -1198,7 +1305,7 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
             return;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if ((st.jit_only || std::getenv("PLB200_EMU_JIT")) && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
+        if ((st.jit_only || st.jit_forms || std::getenv("PLB200_EMU_JIT")) && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
         } else if (st.jit_only) fail("emu: a pass with two-bit pair ops has no specialised source");
         else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
         else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
@@ -1223,7 +1330,8 @@ int emulate_routed_typed(int n, const std::vector<AdjItem> &items, bool scaled, 
         if (st.ext) emulate_pass<T2, Cfg, true>(sv0, nullptr, acc.data(), pp);
         else emulate_pass<T2, Cfg, false>(sv0, nullptr, acc.data(), pp);
     };
-    build_schedule<T2, Cfg>(n, 148, items, scaled, [&](const Step &st, const PassParams<T2> *pp) {
+    const char *jfe = std::getenv("PLB200_JIT_FORMS");
+    build_schedule<T2, Cfg>(n, 148, items, scaled, !(jfe && jfe[0] == '0'), [&](const Step &st, const PassParams<T2> *pp) {
         if (rc) return;
         if (have) plain(held_st, *held), have = false;
         if (st.op >= 0) rc = standalone(ctx, st.op);
@@ -1258,8 +1366,8 @@ void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem>
         if (s.op >= 0) out[1]++;
         else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
     };
-    if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, count);
-    else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, count);
+    if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, false, count);
+    else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, false, count);
 }
 int64_t emu_jit_passes() { return g_emu_jit_passes; }
 void emu_kind_hist(int64_t out[32], bool reset) {

@@ -157,6 +157,27 @@ DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) 
     cmul_ip(a, m2);
     cmul_ip(b, m3);
 }
+// scaled rotations (K_SROT_R / K_SROT_I): 4 FMAs per pair, the cosine / sine is carried by the host
+DEV void srot_r_t(T2 &a, T2 &b, const real t) { // a' = a - t b, b' = b + t a
+    const T2 a0 = a, b0 = b;
+    a.x = fma(-t, b0.x, a0.x), a.y = fma(-t, b0.y, a0.y);
+    b.x = fma(t, a0.x, b0.x), b.y = fma(t, a0.y, b0.y);
+}
+DEV void srot_r_k(T2 &a, T2 &b, const real k) { // a' = k a - b, b' = a + k b
+    const T2 a0 = a, b0 = b;
+    a.x = fma(k, a0.x, -b0.x), a.y = fma(k, a0.y, -b0.y);
+    b.x = fma(k, b0.x, a0.x), b.y = fma(k, b0.y, a0.y);
+}
+DEV void srot_i_t(T2 &a, T2 &b, const real t) { // a' = a - i t b, b' = b - i t a
+    const T2 a0 = a, b0 = b;
+    a.x = fma(t, b0.y, a0.x), a.y = fma(-t, b0.x, a0.y);
+    b.x = fma(t, a0.y, b0.x), b.y = fma(-t, a0.x, b0.y);
+}
+DEV void srot_i_k(T2 &a, T2 &b, const real k) { // a' = i k a + b, b' = a + i k b
+    const T2 a0 = a, b0 = b;
+    a.x = fma(-k, a0.y, b0.x), a.y = fma(k, a0.x, b0.y);
+    b.x = fma(-k, b0.y, a0.x), b.y = fma(k, b0.x, a0.y);
+}
 // adjoint (two-state) passes: Im / Re of conj(a) b in double, and the per-CTA overlap accumulators
 DEV double im_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.y - (double)a.y * (double)b.x; }
 DEV double re_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.x + (double)a.y * (double)b.y; }
@@ -369,17 +390,30 @@ template <typename T2, class Cfg> class Gen {
             if (NS == 2)
                 add("    T2 h%d = *(const T2 *)(c%d + %s);\n", u, low_id(rh.sroff[u] & lowmask), hex(rh.sroff[u] & ~lowmask).c_str());
         }
-        // thread-scalar diagonal factors of this round (K_DIAG_T / K_DIAG1_T): merged when there are >= 2
+        // thread-scalar factors of this round (K_DIAG_T / K_DIAG1_T, ladders on no register bit): merged into ONE
+        // scalar per thread, applied once at the end of the round (it commutes with every op), when there are
+        // >= 2 of them or a ladder among them.  Ladder records may sit among the regular ops (the encoder's
+        // "jit forms") or in the tail section; their entry records are skipped here.
         int n_tscalar = 0;
-        for (int k = 0; k < rh.nops; k++) {
-            const int kind = code_kind(pp.ops[rh.first_op + k].code);
-            if (kind == K_DIAG_T || kind == K_DIAG1_T) n_tscalar++;
+        bool r_ladder = false;
+        for (int k = 0; k < rh.nops + rh.nlad; k++) {
+            const TileOp<T2> &o = pp.ops[rh.first_op + k];
+            const int kind = code_kind(o.code);
+            if (kind == K_LADDER) {
+                if (code_p(o.code) >= R) r_ladder = true;
+                k += ladder_records<T2>(static_cast<int>(o.slot)) - 1;
+            } else if (kind == K_DIAG_T || kind == K_DIAG1_T)
+                n_tscalar++;
         }
-        const bool merge_ts = n_tscalar >= 2;
+        const bool merge_ts = n_tscalar >= 2 || r_ladder;
         if (merge_ts) s += "    T2 ts; ts.x = (real)1; ts.y = (real)0; bool ts_any = false;\n";
 
-        for (int k = 0; k < rh.nops; k++) {
+        for (int k = 0; k < rh.nops + rh.nlad; k++) {
             const int K = rh.first_op + k;
+            if (code_kind(pp.ops[K].code) == K_LADDER) {
+                k += gen_ladder(K) - 1;
+                continue;
+            }
             if (pp.ops[K].code & F_OVL) {
                 gen_overlap(K);
                 continue;
@@ -400,7 +434,6 @@ template <typename T2, class Cfg> class Gen {
             }
             s += "    }\n";
         }
-        gen_ladders(rh);
         // routed stores: swapped bit i of this amplitude selects the destination slab; inside the slab the
         // swapped positions take this rank's global-bit values
         int reg_of_swapped[3] = {-1, -1, -1};
@@ -548,6 +581,14 @@ template <typename T2, class Cfg> class Gen {
             }
             close_cond();
         } break;
+        case K_SROT_R: case K_SROT_I: case K_SROK_R: case K_SROK_I: { // scaled rotations: tangent / cotangent form
+            decl_m(1);
+            open_cond();
+            pairs_on(P, pr);
+            const char *fn = kind == K_SROT_R ? "srot_r_t" : kind == K_SROT_I ? "srot_i_t" : kind == K_SROK_R ? "srot_r_k" : "srot_i_k";
+            for (auto [u0, u1] : pr) add("            %s(%s, %s, m0.x);\n", fn, V(u0).c_str(), V(u1).c_str());
+            close_cond();
+        } break;
         case K_SWAP: case K_SWAP_M: case K_SWAP_CR: case K_SWAP2: case K_SWAP2_M: {
             pr.clear();
             if (kind == K_SWAP2 || kind == K_SWAP2_M) {
@@ -668,35 +709,57 @@ template <typename T2, class Cfg> class Gen {
         s += "    }\n";
     }
 
-    void gen_ladders(const RoundHdr &rh) {
-        const int first = rh.first_op + rh.nops;
-        constexpr int per = ladder_entries_per_record<T2>();
-        for (int q = 0; q < rh.nlad;) {
-            const TileOp<T2> &hd = pp.ops[first + q];
-            const int n = static_cast<int>(hd.slot), p = code_p(hd.code);
-            const LadderEntry<T2> *en = reinterpret_cast<const LadderEntry<T2> *>(&pp.ops[first + q + 1]);
-            add("    { // ladder of %d controlled phases on register bit %d\n", n, p);
-            add("        const LadderEntry *en = (const LadderEntry *)&pp.ops[%d];\n", first + q + 1);
-            s += "        T2 t; t.x = (real)1; t.y = (real)0; bool any = false;\n";
-            for (int e = 0; e < n; e++) {
-                std::string c;
-                if (en[e].cmask_o) c = "((base & en[" + std::to_string(e) + "].cmask_o) == en[" + std::to_string(e) + "].cmask_o)";
-                if (en[e].cm_tid) {
-                    if (!c.empty()) c += " && ";
-                    c += "((tid & " + hex(en[e].cm_tid) + ") == " + hex(en[e].cm_tid) + ")";
-                }
-                if (c.empty()) add("        cmul_ip(t, en[%d].ph); any = true;\n", e);
-                else add("        if (%s) { cmul_ip(t, en[%d].ph); any = true; }\n", c.c_str(), e);
+    // One ladder (header record K + packed entries): the thread multiplies the phases of its active entries into
+    // one scalar and applies it to the registers whose bit p is set; p == R (no register bit): the scalar joins
+    // the round's thread scalar `ts`.  Returns the number of records.
+    int gen_ladder(int K) {
+        const TileOp<T2> &hd = pp.ops[K];
+        const int n = static_cast<int>(hd.slot), p = code_p(hd.code);
+        const LadderEntry<T2> *en = reinterpret_cast<const LadderEntry<T2> *>(&pp.ops[K + 1]);
+        const bool to_ts = p >= R;
+        add("    { // ladder of %d controlled phases on register bit %d\n", n, p);
+        add("        const LadderEntry *en = (const LadderEntry *)&pp.ops[%d];\n", K + 1);
+        auto cond_of_entry = [&](int e) {
+            std::string c;
+            if (en[e].cmask_o) c = "((base & en[" + std::to_string(e) + "].cmask_o) == en[" + std::to_string(e) + "].cmask_o)";
+            if (en[e].cm_tid) {
+                if (!c.empty()) c += " && ";
+                c += "((tid & " + hex(en[e].cm_tid) + ") == " + hex(en[e].cm_tid) + ")";
             }
-            s += "        if (any) {\n";
-            for (int u = 0; u < NV; u++)
-                if (p >= R || ((u >> p) & 1)) {
-                    add("            cmul_ip(%s, t);\n", Vs('v', u).c_str());
-                    if (NS == 2) add("            cmul_ip(%s, t);\n", Vs('h', u).c_str());
-                }
-            s += "        }\n    }\n";
-            q += 1 + (n + per - 1) / per;
+            return c;
+        };
+        if (to_ts) {
+            for (int e = 0; e < n; e++) {
+                const std::string c = cond_of_entry(e);
+                if (c.empty()) add("        cmul_ip(ts, en[%d].ph); ts_any = true;\n", e);
+                else add("        if (%s) { cmul_ip(ts, en[%d].ph); ts_any = true; }\n", c.c_str(), e);
+            }
+            s += "    }\n";
+            return ladder_records<T2>(n);
         }
+        // unconditional entries first: the scalar starts as their product and is always applied
+        bool have_t = false;
+        for (int e = 0; e < n; e++) {
+            if (!cond_of_entry(e).empty()) continue;
+            if (!have_t) add("        T2 t = en[%d].ph;\n", e);
+            else add("        cmul_ip(t, en[%d].ph);\n", e);
+            have_t = true;
+        }
+        const bool always = have_t;
+        if (!have_t) s += "        T2 t; t.x = (real)1; t.y = (real)0; bool any = false;\n";
+        for (int e = 0; e < n; e++) {
+            const std::string c = cond_of_entry(e);
+            if (c.empty()) continue;
+            add("        if (%s) { cmul_ip(t, en[%d].ph);%s }\n", c.c_str(), e, always ? "" : " any = true;");
+        }
+        s += always ? "        {\n" : "        if (any) {\n";
+        for (int u = 0; u < NV; u++)
+            if ((u >> p) & 1) {
+                add("            cmul_ip(%s, t);\n", Vs('v', u).c_str());
+                if (NS == 2) add("            cmul_ip(%s, t);\n", Vs('h', u).c_str());
+            }
+        s += "        }\n    }\n";
+        return ladder_records<T2>(n);
     }
 
     // resident CTAs per SM the kernel is compiled for (register cap); PLB200_JIT_MINB overrides (tuning)

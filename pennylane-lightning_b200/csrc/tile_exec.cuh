@@ -130,6 +130,18 @@ enum : int {
     // for the registers with umask set.  Only the SPECIALISED kernels implement it (jit_codegen.hpp): a pass
     // holding one is never handed to the interpreter.
     K_PAIR2 = 26,
+    // SCALED rotations (specialised kernels only, "jit forms" of the encoder): an uncontrolled rotation leaves its
+    // cosine (or sine) with the host-carried scalar, so a pair costs 4 FMAs instead of the 6 of three shears:
+    //   K_SROT_R: c [[1, -t], [t, 1]]   a' = a - t b, b' = b + t a      t = m[0].x = tan
+    //   K_SROK_R: s [[k, -1], [1, k]]   a' = k a - b, b' = a + k b      k = m[0].x = cot
+    // K_SROT_I / K_SROK_I are the RX-like twins [[1, -it], [-it, 1]] / [[ik, 1], [1, ik]].  The tangent form is
+    // used for every angle whose tangent stays below 2^16 (the stored amplitudes grow by 1 / cos, floating point
+    // keeps their relative precision, the encoder bounds the growth inside a round), so the structure of a pass
+    // does not depend on its angles except within 2e-5 of a half turn, where the cotangent form takes over.
+    K_SROT_R = 27,
+    K_SROT_I = 28,
+    K_SROK_R = 29,
+    K_SROK_I = 30,
     K_LAST_OVL = K_OVL_D,
     K_FIRST_DIAG = K_DIAG_R,
     K_FIRST_OVL = K_OVL_X,
@@ -142,7 +154,7 @@ constexpr uint32_t F_OVL = 1u << 22;  // adjoint overlap op
 PLB_HD constexpr int kind_cases(int kind) {
     return (kind == K_DIAG_PP || kind == K_SWAP_CR || kind == K_DIAG_CR || kind == K_SWAP2 || kind == K_SWAP2_M)
                ? kMaxR * (kMaxR - 1)
-           : (kind == K_LADDER || kind == K_PAIR2)                         ? 0
+           : (kind == K_LADDER || kind >= K_PAIR2) ? 0
            : (kind == K_DIAG_T || kind == K_DIAG1_T || kind == K_DIAG_G) ? 1
                                                                         : kMaxR;
 }

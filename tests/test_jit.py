@@ -262,3 +262,90 @@ def test_jit_two_bit_pair_ops_fused(plb, ref, jit_sync, dtype):
     r.apply_ops(ops)
     assert a.last_apply_stats()[1] == stats[0]
     np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=TOL[np.dtype(dtype)])
+
+
+def _emu_lib():
+    import subprocess
+
+    from test_tile_emulation import CSRC, EMU
+
+    res = subprocess.run(["make", "-C", CSRC, "-j8", "emu"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    emu = C.CDLL(EMU)
+    emu.plb200_emu_last_error.restype = C.c_char_p
+    emu.plb200_emu_jit_passes.restype = C.c_int64
+    return emu
+
+
+K_LADDER, K_SROT_R, K_SROT_I, K_SROK_R, K_SROK_I = 22, 27, 28, 29, 30
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_jit_forms_scaled_rotations_and_in_stream_ladders(plb, dtype, monkeypatch):
+    """The encoder's "jit forms" (fusion.cu build_schedule, jit_forms = true): uncontrolled RX / RY as scaled
+    rotations (tangent form, cotangent form at half turns), controlled two-valued diagonals split into controlled
+    phases, phases sharing a register bit merged into in-stream ladders.  The generated code on host memory must
+    give the oracle's amplitudes, and the same tape in the interpreter's forms must not contain those kinds."""
+    from test_tile_emulation import emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    n = 15 if dtype == np.complex128 else 16
+    rng = np.random.default_rng(17)
+    special = [np.pi, -np.pi, 3 * np.pi, np.pi - 1e-7, np.pi + 1e-9, 0.0, 2 * np.pi, np.pi / 2, 1e-9]
+    ops = []
+    for layer in range(8):
+        for w in range(n):
+            th = special[int(rng.integers(len(special)))] if rng.random() < 0.3 else rng.uniform(0, 2 * np.pi)
+            ops.append(circuits.op(("RX", "RY", "RZ")[int(rng.integers(3))], [w], [th], inverse=bool(rng.integers(2))))
+        p = rng.permutation(n)
+        for i in range(0, n - 1, 2):
+            nm = ("CNOT", "CRZ", "CRZ", "ControlledPhaseShift", "CZ")[int(rng.integers(5))]
+            ops.append(circuits.op(nm, [int(p[i]), int(p[i + 1])], [rng.uniform(0, 6)] if nm in ("CRZ", "ControlledPhaseShift") else []))
+    st = random_state(n, dtype, 3)
+    expect = oracle_apply(n, ops, st)
+    hist = (C.c_int64 * 32)()
+    # the interpreter's forms: none of the specialised kinds, no in-stream ladders of fewer than six entries
+    monkeypatch.delenv("PLB200_EMU_JIT", raising=False)
+    emu.plb200_emu_kind_histogram(hist, 1)
+    out, _ = emu_apply(emu, plb, n, ops, st)
+    emu.plb200_emu_kind_histogram(hist, 1)
+    np.testing.assert_allclose(out, expect, rtol=0, atol=4 * TOL[np.dtype(dtype)])
+    assert hist[K_SROT_R] + hist[K_SROT_I] + hist[K_SROK_R] + hist[K_SROK_I] == 0
+    # the specialised forms
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    before = emu.plb200_emu_jit_passes()
+    out, stats = emu_apply(emu, plb, n, ops, st)
+    emu.plb200_emu_kind_histogram(hist, 1)
+    assert emu.plb200_emu_jit_passes() > before and stats[1] == 0
+    np.testing.assert_allclose(out, expect, rtol=0, atol=4 * TOL[np.dtype(dtype)])
+    assert hist[K_SROT_R] > 0 and hist[K_SROT_I] > 0, list(hist)
+    assert hist[K_SROK_R] + hist[K_SROK_I] > 0, list(hist)  # the exact half turns
+    assert hist[K_LADDER] > 0, list(hist)
+    # PLB200_JIT_FORMS=0 keeps the specialised kernels on the interpreter's encoding
+    monkeypatch.setenv("PLB200_JIT_FORMS", "0")
+    out, _ = emu_apply(emu, plb, n, ops, st)
+    emu.plb200_emu_kind_histogram(hist, 1)
+    np.testing.assert_allclose(out, expect, rtol=0, atol=4 * TOL[np.dtype(dtype)])
+    assert hist[K_SROT_R] + hist[K_SROT_I] == 0
+
+
+def test_jit_forms_growth_stays_bounded_c64(plb, monkeypatch):
+    """600 rotations with angles a hair away from a half turn (tangents up to 2^16): the stored amplitudes of the
+    tangent form grow by 1 / cos per rotation; the encoder must fold the carried scalar back / switch to the
+    cotangent form before fp32 overflows."""
+    from test_tile_emulation import emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 16
+    rng = np.random.default_rng(5)
+    ops = []
+    for _ in range(600):
+        th = np.pi + rng.choice([-1, 1]) * 10 ** rng.uniform(-6, -1)
+        ops.append(circuits.op(("RX", "RY")[int(rng.integers(2))], [int(rng.integers(n))], [th]))
+        if rng.random() < 0.2:
+            ops.append(circuits.op("CNOT", [int(x) for x in rng.permutation(n)[:2]]))
+    st = random_state(n, np.complex64, 8)
+    out, _ = emu_apply(emu, plb, n, ops, st)
+    assert np.all(np.isfinite(out.view(np.float32)))
+    np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=5e-5)
