@@ -572,6 +572,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         };
         Step st;
         int op_cursor = 0;
+        double pass_growth = 1.0; // growth of the stored amplitudes by this pass's scaled rotations
         for (size_t r = 0; r < hp.rounds.size(); r++) {
             std::vector<int> rl; // local positions of the register bits, ascending
             for (int i = 0; i < M; i++)
@@ -640,7 +641,6 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     if (local_mask >> tpos[i] & 1) m |= 1u << i;
                 return m;
             };
-            double round_growth = 1.0; // growth of the stored amplitudes by this round's scaled rotations
             auto reg_of_local = [&](int lp) { return static_cast<int>(std::find(rl.begin(), rl.end(), lp) - rl.begin()); };
             auto reg_pos = [&](int global_bit) { return reg_of_local(local_of[global_bit]); };
             auto roff_of = [&](int u) {
@@ -739,9 +739,17 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                     const int p = reg_pos(it.op.tbits[0]);
                     // tangent-form rotations let the stored amplitudes grow by 1 / |cos|: at most 2^16 per
                     // rotation and 2^40 (c64) / 2^400 (c128) per round on top of the carried scalar's own range
-                    const PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0, jf,
-                                                  std::min(0x1p16, (is_double ? 0x1p400 : 0x1p40) / round_growth));
-                    if (pf.kind >= K_SROT_R && pf.kind <= K_SROK_I) st.jit_forms = true, round_growth /= std::abs(pf.s);
+                    // tangent-form rotations let the stored amplitudes grow by 1 / |cos|: at most 2^16 per
+                    // rotation and 2^60 (c64) / 2^400 (c128) per pass on top of the carried scalar's own range;
+                    // past 2^20 more (cotangent forms grow by < sqrt 2 each) the three shears take over
+                    PairForm pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0, jf,
+                                            std::min(0x1p16, (is_double ? 0x1p400 : 0x1p60) / pass_growth));
+                    if (pf.kind >= K_SROT_R && pf.kind <= K_SROK_I) {
+                        if (pass_growth / std::abs(pf.s) > (is_double ? 0x1p420 : 0x1p80))
+                            pf = pair_form(it.op.blocks[0].m, allow_scaled && cmask == 0, false);
+                        else
+                            st.jit_forms = true, pass_growth /= std::abs(pf.s);
+                    }
                     const bool masked = cm_reg != 0;
                     auto masked_kind = [](int k) {
                         return k == K_LIFT_R ? K_LIFT_R_M : k == K_LIFT_I ? K_LIFT_I_M : k == K_LU_R ? K_LU_R_M
@@ -890,11 +898,15 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             }
             for (int bk = 0; bk <= R; bk++)
                 if (jf || bucket[bk].size() < kMinLadder) flush_bucket(bk);
-            const bool last_round = r + 1 == hp.rounds.size();
-            const double mag = std::abs(sigma);
-            if (sigma != cd(1.0) && (mag < sig_lo || mag > sig_hi || (last_round && (Cfg::NS == 2 || tape_done)))) {
-                top[op_cursor++] = scale_op(sigma);
-                sigma = cd(1.0);
+            // The carried scalar has ONE slot per pass, at the end of its last round, whether it is folded back
+            // there (adjoint passes, the end of the tape, |sigma| about to leave its range) or not (the slot then
+            // holds 1 and the specialised kernels skip it): the structure of a pass — the key of its compiled
+            // kernel — must not depend on the angles of the passes before it.
+            if (r + 1 == hp.rounds.size()) {
+                const double mag = std::abs(sigma);
+                const bool fold = sigma != cd(1.0) && (Cfg::NS == 2 || tape_done || mag < sig_lo || mag > sig_hi);
+                top[op_cursor++] = scale_op(fold ? sigma : cd(1.0));
+                if (fold) sigma = cd(1.0);
             }
             rh[r].nops = op_cursor - rh[r].first_op;
             for (int bk = 0; bk <= R; bk++) {
@@ -1203,15 +1215,30 @@ void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector
     const auto items = as_items(ops);
     const char *jfe = std::getenv("PLB200_JIT_FORMS");
     const bool jit_forms = !(jfe && jfe[0] == '0'); // what the specialised tier compiles
+    // PLB200_DUMP_REFUSE=1 (tests): every pass in the specialised forms is refused after its source was taken, as
+    // the asynchronous tier does on a first sighting — the carried scalar then follows the interpreter's forms;
+    // the sources must not depend on which way it went
+    const bool refuse = std::getenv("PLB200_DUMP_REFUSE") != nullptr;
     out.clear();
-    if (precision == 64)
-        build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<double2> *pp) {
-            if (s.op == -1) out.push_back(jit::generate_pass_source<double2, FwdCfg<double2>>(*pp));
+    auto run = [&](auto t2, auto cfg) {
+        using T2 = decltype(t2);
+        using Cfg = decltype(cfg);
+        build_schedule<T2, Cfg>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<T2> *pp) -> bool {
+            if (s.op != -1) return true;
+            if (jit_forms && !s.jit_forms && refuse && !out.empty() && out.back() == "\x01") { // the interpreter encoding of a refused pass
+                out.pop_back();
+                return true;
+            }
+            out.push_back(jit::generate_pass_source<T2, Cfg>(*pp));
+            if (refuse && s.jit_forms) {
+                out.push_back("\x01");
+                return false;
+            }
+            return true;
         });
-    else
-        build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<float2> *pp) {
-            if (s.op == -1) out.push_back(jit::generate_pass_source<float2, FwdCfg<float2>>(*pp));
-        });
+    };
+    if (precision == 64) run(double2{}, FwdCfg<double2>{});
+    else run(float2{}, FwdCfg<float2>{});
 }
 
 bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const std::vector<int64_t> &tp,

@@ -116,6 +116,27 @@ DEV void lu_r(T2 &a, T2 &b, const T2 m0, const T2 m1) {
     a = __fmul2_rn(a, f2(m1.x, m1.x));
     b = __fmul2_rn(b, f2(m1.y, m1.y));
 }
+// scaled rotations: TWO packed FMAs per pair
+DEV void srot_r_t(T2 &a, T2 &b, const real t) {
+    const T2 a0 = a, b0 = b;
+    a = __ffma2_rn(f2(-t, -t), b0, a0);
+    b = __ffma2_rn(f2(t, t), a0, b0);
+}
+DEV void srot_r_k(T2 &a, T2 &b, const real k) {
+    const T2 a0 = a, b0 = b;
+    a = __ffma2_rn(f2(k, k), a0, f2(-b0.x, -b0.y));
+    b = __ffma2_rn(f2(k, k), b0, a0);
+}
+DEV void srot_i_t(T2 &a, T2 &b, const real t) {
+    const T2 a0 = a, b0 = b;
+    a = __ffma2_rn(f2(t, t), f2(b0.y, -b0.x), a0);
+    b = __ffma2_rn(f2(t, t), f2(a0.y, -a0.x), b0);
+}
+DEV void srot_i_k(T2 &a, T2 &b, const real k) {
+    const T2 a0 = a, b0 = b;
+    a = __ffma2_rn(f2(k, k), f2(-a0.y, a0.x), b0);
+    b = __ffma2_rn(f2(k, k), f2(-b0.y, b0.x), a0);
+}
 #else
 DEV void cmul_ip(T2 &v, const T2 d) {
     const real t = v.x * d.y;
@@ -150,13 +171,6 @@ DEV void lu_r(T2 &a, T2 &b, const T2 m0, const T2 m1) {
     a.x = a.x * m1.x, a.y = a.y * m1.x;
     b.x = b.x * m1.y, b.y = b.y * m1.y;
 }
-#endif
-DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) {
-    cshear_ip(a, m0, b);
-    cshear_ip(b, m1, a);
-    cmul_ip(a, m2);
-    cmul_ip(b, m3);
-}
 // scaled rotations (K_SROT_R / K_SROT_I): 4 FMAs per pair, the cosine / sine is carried by the host
 DEV void srot_r_t(T2 &a, T2 &b, const real t) { // a' = a - t b, b' = b + t a
     const T2 a0 = a, b0 = b;
@@ -177,6 +191,13 @@ DEV void srot_i_k(T2 &a, T2 &b, const real k) { // a' = i k a + b, b' = a + i k 
     const T2 a0 = a, b0 = b;
     a.x = fma(-k, a0.y, b0.x), a.y = fma(k, a0.x, b0.y);
     b.x = fma(-k, b0.y, a0.x), b.y = fma(k, b0.x, a0.y);
+}
+#endif
+DEV void lu_c(T2 &a, T2 &b, const T2 m0, const T2 m1, const T2 m2, const T2 m3) {
+    cshear_ip(a, m0, b);
+    cshear_ip(b, m1, a);
+    cmul_ip(a, m2);
+    cmul_ip(b, m3);
 }
 // adjoint (two-state) passes: Im / Re of conj(a) b in double, and the per-CTA overlap accumulators
 DEV double im_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.y - (double)a.y * (double)b.x; }
@@ -684,6 +705,8 @@ template <typename T2, class Cfg> class Gen {
             }
             std::string c2 = cond;
             if (kind == K_DIAG1_T) c2 = c2.empty() ? "pt" : "(" + c2 + ") && pt";
+            // the pass's slot for the host-carried scalar: holds 1 unless the scalar is folded back here
+            if (kind == K_DIAG_T && cond.empty() && par.empty()) c2 = "m0.x != (real)1 || m0.y != (real)0";
             if (!c2.empty()) s += "        if (" + c2 + ") {\n";
             if (kind != K_DIAG_CT && merge_ts) {
                 if (last) s += "            cmul_ip(ts, d); ts_any = true;\n";

@@ -349,3 +349,34 @@ def test_jit_forms_growth_stays_bounded_c64(plb, monkeypatch):
     out, _ = emu_apply(emu, plb, n, ops, st)
     assert np.all(np.isfinite(out.view(np.float32)))
     np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=5e-5)
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_pass_sources_do_not_depend_on_angles_or_on_refusals(plb, prec, monkeypatch, tmp_path):
+    """The structure key of a compiled pass is its generated text.  It must be the same (a) for every parameter set
+    of a variational circuit — the carried scalar has one slot per pass whether it is folded back there or not,
+    tangent-form rotations do not switch form with the angle — and (b) whether earlier passes ran in the
+    specialised forms or were refused (asynchronous tier, first sightings) and ran in the interpreter's."""
+    n = 26
+
+    def sources(ops, sub, refuse):
+        out = tmp_path / sub
+        out.mkdir()
+        if refuse:
+            monkeypatch.setenv("PLB200_DUMP_REFUSE", "1")
+        else:
+            monkeypatch.delenv("PLB200_DUMP_REFUSE", raising=False)
+        blob = plb.OpsBlob(ops)
+        npass = C.c_int64()
+        rc = plb.lib().plb200_jit_dump_sources(C.c_int64(n), prec, blob.ptr(), str(out).encode(), C.byref(npass))
+        assert rc == 0, plb.lib().plb200_last_error()
+        return [(out / f"pass_{i}.cu").read_text() for i in range(npass.value)]
+
+    ops = circuits.random_circuit(n, 12, 77)
+    rng = np.random.default_rng(3)
+    ops2 = [dict(o, params=[float(rng.uniform(0, 2 * np.pi)) for _ in o["params"]]) for o in ops]
+    a = sources(ops, "a", False)
+    assert len(a) >= 5 and all("srot_" in t for t in a[:3])
+    assert sources(ops, "b", True) == a
+    assert sources(ops2, "c", False) == a
+    assert sources(ops2, "d", True) == a
