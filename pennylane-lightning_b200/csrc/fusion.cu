@@ -510,7 +510,8 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 const AdjItem &it = items[i];
                 if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() == 2 && !is_swap2(it.op))
                     emitted += 2 * it.op.blocks.size(); // K_PAIR2: one record per block (+ a pivot each at most)
-                else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG)
+                else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG && it.op.cmask != 0 &&
+                         __builtin_popcountll(f[i].pmask) == 1 && f[i].d[0] != cd(1.0))
                     emitted += 2; // a controlled two-valued diagonal may split into two controlled phases
                 else
                     emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
