@@ -243,6 +243,20 @@ class LocalEngine:
     def host_state(self):
         return self.sv.get_state()
 
+    # ---- linear algebra between slabs with the same layout (sharded adjoint: lambda, H lambda, mu)
+    def copy_from(self, other):
+        self.sv.copy_from(other.sv)
+
+    def axpy(self, alpha, other):
+        self.sv.axpy(alpha, other.sv)
+
+    def dot(self, other):
+        """local part of <self|other>"""
+        return self.sv.dot(other.sv)
+
+    def apply_generator(self, name, wires, adj, ctrl_wires, ctrl_values):
+        return self.sv.apply_generator(name, wires, adj, ctrl_wires, ctrl_values)
+
     @property
     def kernel_launches(self):
         return self.sv.kernel_launches
@@ -255,6 +269,7 @@ class DistStateVector:
 
         self.dist, self.torch = dist, torch
         self.group = group
+        self._ctor = (engine_factory, swap)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.g = int(np.log2(self.world))
@@ -703,6 +718,109 @@ class DistStateVector:
         parts = [None] * self.world
         self.dist.all_gather_object(parts, bits, group=self.group)
         return np.concatenate(parts, axis=0)
+
+    # -- adjoint Jacobian on the sharded state (AdjointJacobianGPUMPI.hpp / AdjointJacobianLQubit.hpp:347-491:
+    #    lambda = U psi, H lambda per observable, reverse sweep with jac = -2 s Im<H lambda| G |lambda>)
+    def clone(self, copy_state=True):
+        """Collective: another sharded vector with the same wire map (and, with copy_state, the same amplitudes)."""
+        factory, swap = self._ctor
+        other = DistStateVector(self.n, self.dtype, engine_factory=factory, group=self.group, swap=swap)
+        other.phys = list(self.phys)
+        if copy_state:
+            other.engine.copy_from(self.engine)
+        else:
+            other.engine.zero()
+        return other
+
+    def _assign(self, src):
+        """self <- src (same world, same size): amplitudes and wire map"""
+        self.phys = list(src.phys)
+        self.engine.copy_from(src.engine)
+
+    def inner(self, other):
+        """<self|other> of two vectors with the same wire map: local dot + all_reduce"""
+        if self.phys != other.phys:
+            raise ValueError("inner product of sharded vectors with different wire maps")
+        z = complex(self.engine.dot(other.engine))
+        out = self._allreduce([z.real, z.imag])
+        return complex(out[0], out[1])
+
+    def _apply_pauli_word(self, word, wires):
+        gates = [dict(name={"X": "PauliX", "Y": "PauliY", "Z": "PauliZ"}[c], wires=[w], params=[], inverse=False,
+                      ctrl_wires=[], ctrl_values=[]) for c, w in zip(word, wires) if c != "I"]
+        self.apply_ops(gates, fuse=False)
+
+    def adjoint_jacobian(self, ops, trainable_params, observables):
+        """Jacobian d<H_j>/d theta_p of the tape `ops` from |0...0>, for Hamiltonians of Pauli words
+        `observables` = [(coeffs, words, wires), ...] and the trainable parameter indices `trainable_params`
+        (indices into the tape's parametrised ops, as JacobianData's; one-parameter ops only).  Returns an array
+        (len(observables), len(trainable_params)), identical on every rank.
+
+        Every vector involved (lambda, one H lambda per observable, the scratch mu) is a sharded vector of this
+        world; they are kept on ONE wire map by giving them the same sequence of operations — exchange decisions
+        depend only on the tape and the map — so slab-local axpy / dot are meaningful.  Before a trainable op's
+        generator is applied all its target wires are made local; a control on a global wire is a rank test."""
+        tp = sorted(int(t) for t in trainable_params)
+        n_par_ops = sum(1 for o in ops if len(o.get("params", ())) > 0)
+        if any(t < 0 or t >= n_par_ops for t in tp):
+            raise ValueError("trainable parameter index out of range")
+        for o in ops:
+            if len(o.get("params", ())) > 1:
+                raise ValueError("The operation is not supported using the adjoint differentiation method")
+        lam = self.clone(copy_state=False)
+        lam.reset()
+        lam.apply_ops(ops, fuse=True)
+        mu = lam.clone(copy_state=False)
+        hls = []
+        for coeffs, words, wires in observables:
+            hl = lam.clone(copy_state=False)
+            for c, word, ws in zip(coeffs, words, wires):
+                xy = [w for ch, w in zip(word, ws) if ch in "XY"]
+                for v in [lam] + hls + [hl]:  # same call on every vector: the maps stay equal
+                    v._make_wires_local(xy)
+                mu._assign(lam)
+                mu._apply_pauli_word(word, ws)
+                assert mu.phys == hl.phys == lam.phys
+                hl.engine.axpy(complex(c), mu.engine)
+            hls.append(hl)
+        jac = np.zeros((len(observables), len(tp)))
+        tpi, cur = len(tp) - 1, n_par_ops - 1
+        for o in reversed(ops):
+            if o["name"] in ("StatePrep", "BasisState"):
+                continue
+            if tpi < 0:
+                break
+            if len(o.get("params", ())) > 0:
+                if cur == tp[tpi]:
+                    nop = normalize_op(o)
+                    if nop["matrix"] is not None:
+                        raise ValueError("The operation is not supported using the adjoint differentiation method")
+                    for v in [lam] + hls:
+                        v._make_wires_local(list(nop["targets"]))
+                    mu._assign(lam)
+                    cw, cv, dead = [], [], False
+                    for w, val in zip(nop["ctrl_wires"], nop["ctrl_values"]):
+                        if mu._is_global(w):
+                            dead = dead or mu._rank_bit(w) != int(val)
+                        else:
+                            cw.append(mu._lw(w)), cv.append(bool(val))
+                    # the generator of "control (x) base" is projector (x) generator(base), same scale factor
+                    scale = mu.engine.apply_generator(nop["base"], [mu._lw(w) for w in nop["targets"]], False, cw, cv)
+                    if dead:
+                        mu.engine.zero()
+                    sign = -1.0 if nop["inverse"] else 1.0
+                    for j, hl in enumerate(hls):
+                        jac[j, tpi] = -2.0 * sign * scale * hl.inner(mu).imag
+                    tpi -= 1
+                cur -= 1
+            if tpi < 0:
+                break
+            inv = dict(o, inverse=not o.get("inverse", False))
+            for v in [lam] + hls:
+                v.apply_ops([inv], fuse=False)
+        for v in [lam, mu] + hls:
+            v.close()
+        return jac
 
     def gather_state(self):
         """Full state in logical wire order on every rank (tests, small n only)."""

@@ -63,6 +63,19 @@ class NumpyEngine:
     def host_state(self):
         return self.sv.state.copy()
 
+    def copy_from(self, other):
+        self.sv.state[:] = other.sv.state
+
+    def axpy(self, alpha, other):
+        self.sv.state += alpha * other.sv.state
+
+    def dot(self, other):
+        return complex(np.vdot(self.sv.state, other.sv.state))
+
+    def apply_generator(self, name, wires, adj, ctrl_wires, ctrl_values):
+        self.launches += 1
+        return self.sv.apply_generator(name, wires, adj, ctrl_wires, ctrl_values)
+
     @property
     def kernel_launches(self):
         return self.launches
@@ -288,3 +301,79 @@ def run_ranks(world, n, seed, backend="gloo", port=29611, swap="auto"):
     for p in procs:
         p.join(timeout=60)
     return res
+
+
+def adjoint_case(n, seed):
+    """Tape (one-parameter gates incl. controlled ones on every wire position), trainable subset, two Hamiltonians."""
+    from pennylane_lightning_b200 import circuits
+
+    rng = np.random.default_rng(seed)
+    ops = []
+    for layer in range(3):
+        for w in range(n):
+            ops.append(circuits.op(("RX", "RY", "RZ", "PhaseShift")[int(rng.integers(4))], [w], [rng.uniform(0, 6)],
+                                   inverse=bool(rng.integers(2))))
+        p = [int(x) for x in rng.permutation(n)]
+        for i in range(0, n - 1, 2):
+            nm = ("CNOT", "CRX", "CRY", "CRZ", "IsingXX", "IsingZZ", "ControlledPhaseShift", "CZ")[int(rng.integers(8))]
+            ops.append(circuits.op(nm, [p[i], p[i + 1]], [rng.uniform(0, 6)] if nm not in ("CNOT", "CZ") else []))
+        ops.append(circuits.op("RY", [p[0]], [rng.uniform(0, 6)], ctrl_wires=[p[1], p[2]], ctrl_values=[True, False]))
+    n_par = sum(1 for o in ops if o["params"])
+    tp = sorted(int(x) for x in rng.choice(n_par, size=(2 * n_par) // 3, replace=False))
+    obs = []
+    for k in range(2):
+        co, words, wires = circuits.pauli_hamiltonian(n, 5, seed + 10 * k)
+        obs.append((co, words, wires))
+    return ops, tp, obs
+
+
+def worker_adjoint(rank, world, n, seed, port, backend, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    from pennylane_lightning_b200.dist import DistStateVector
+
+    try:
+        if backend == "nccl":
+            torch.cuda.set_device(rank)
+            os.environ["PLB200_JIT_MIN_QUBITS"] = "12"
+        sv = DistStateVector(n, np.complex128, engine_factory=NumpyEngine if backend == "gloo" else None)
+        ops, tp, obs = adjoint_case(n, seed)
+        jac = sv.adjoint_jacobian(ops, tp, obs)
+        if rank == 0:
+            q.put(dict(jac=jac))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_ranks_adjoint(world, n, seed, backend="gloo", port=29720):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker_adjoint, args=(r, world, n, seed, port, backend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=60)
+    return res
+
+
+def check_adjoint(res, n, seed):
+    from oracle import np_oracle
+
+    ops, tp, obs = adjoint_case(n, seed)
+    name = {"X": "PauliX", "Y": "PauliY", "Z": "PauliZ"}
+    hams = []
+    for co, words, wires in obs:
+        terms = []
+        for word, ws in zip(words, wires):
+            named = [np_oracle.Observable.named(name[c], [w]) for c, w in zip(word, ws)]
+            terms.append(named[0] if len(named) == 1 else np_oracle.Observable.tensor(named))
+        hams.append(np_oracle.Observable.hamiltonian(co, terms))
+    expect = np.asarray(np_oracle.StateVector(n, np.complex128).adjoint_jacobian(hams, ops, tp, apply_ops=True))
+    np.testing.assert_allclose(res["jac"], expect.reshape(len(hams), len(tp)), rtol=0, atol=1e-11)

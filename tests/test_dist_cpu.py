@@ -77,3 +77,12 @@ def test_sharded_measurements(world, n, seed):
     """Pauli-word / Hamiltonian expval (X/Y on global wires are swapped in), probs marginals in the given wire
     order, and sampling on the sharded state, against the single-process oracle on the gathered state."""
     check_measurements(run_ranks_measure(world, n, seed, "gloo", port=29690 + seed), n)
+
+
+@pytest.mark.parametrize("world,n,seed", [(2, 6, 3), (4, 7, 4)])
+def test_sharded_adjoint_jacobian(world, n, seed):
+    """Adjoint Jacobian with lambda, H lambda and mu sharded over the ranks and kept on one wire map
+    (AdjointJacobianGPUMPI.hpp semantics) against the single-process oracle's adjoint loop."""
+    from dist_helpers import check_adjoint, run_ranks_adjoint
+
+    check_adjoint(run_ranks_adjoint(world, n, seed, "gloo", port=29730 + seed), n, seed)

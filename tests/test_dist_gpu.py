@@ -44,3 +44,15 @@ def test_sharded_measurements_gpu(world):
         pytest.skip(f"needs {world} GPUs")
     n = 16
     check_measurements(run_ranks_measure(world, n, 3, "nccl", port=29760 + world), n)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_adjoint_jacobian_gpu(world):
+    """Adjoint Jacobian with lambda / H lambda / mu sharded over GPUs (routed exchanges keep the vectors on one
+    wire map) against the oracle's single-process adjoint loop."""
+    from dist_helpers import check_adjoint, run_ranks_adjoint
+
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, seed = 14, 5
+    check_adjoint(run_ranks_adjoint(world, n, seed, "nccl", port=29780 + world), n, seed)
