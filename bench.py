@@ -279,6 +279,31 @@ def extra_qft(plb, circuits, n, dtype, tag, stream, peak):
             "tolerance": tol, "pass": bool(err <= tol)}
 
 
+def extra_sampling(plb, circuits, stream, peak, n=30, shots=100000):
+    """Computational-basis samples of the config-2 state with the table-free device sampler (one sweep for the chunk
+    masses, a scan, one warp per shot); checked through every single-wire marginal against <Z_w>."""
+    import torch
+
+    sv = plb.StateVector(n, np.complex128, torch.cuda.current_device(), stream)
+    sv.apply_ops(plb.OpsBlob(circuits.random_circuit(n, DEPTH, SEED)), fuse=True)
+    sv.sync()
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        s = sv.generate_samples(shots, seed=5, device=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    z = np.asarray(sv.expval_pauli_words_each(["Z"] * n, [[w] for w in range(n)]))
+    err = float(np.max(np.abs((1.0 - 2.0 * s.mean(axis=0)) - z)))
+    S = (1 << n) * 16
+    del sv
+    return {"qubits": n, "shots": shots, "seconds": best, "shots_per_s": shots / best,
+            "roofline_frac_of_one_sweep": S / best / 1e9 / peak,
+            "max_abs_err_single_wire_marginals_vs_expval_z": err, "tolerance": 5.0 / np.sqrt(shots),
+            "pass": bool(err <= 5.0 / np.sqrt(shots)),
+            "what": "plb200_generate_samples_device, samples returned to the host (shots x n uint64)"}
+
+
 def extra_adjoint(plb, lq_ref, circuits, stream, peak, n=24, n_params=1000, ref_params=40):
     import torch
 
@@ -707,7 +732,8 @@ def run_ours(args):
             extra = {}
             for key, fn in (("config3_qft33_c128", lambda: extra_qft(plb, circuits, 33, np.complex128, "c128", stream, peak)),
                             ("config3_qft33_c64", lambda: extra_qft(plb, circuits, 33, np.complex64, "c64", stream, peak)),
-                            ("config5_adjoint_24q_1000", lambda: extra_adjoint(plb, lq_ref, circuits, stream, peak))):
+                            ("config5_adjoint_24q_1000", lambda: extra_adjoint(plb, lq_ref, circuits, stream, peak)),
+                            ("sampling_30q_device", lambda: extra_sampling(plb, circuits, stream, peak, nloc))):
                 try:
                     extra[key] = fn()
                 except Exception as exc:

@@ -206,9 +206,14 @@ int plb200_expval_obs(plb200_sv *sv, const plb200_obs *obs, double *out);
 int plb200_var_obs(plb200_sv *sv, const plb200_obs *obs, double *out);
 /* alias-method sampling with std::mt19937(seed) exactly as MeasurementKernels.hpp:308-381;
  * seed < 0 => std::random_device.  out: shots x n_wires uint64 (wire order as given);
- * n_wires < 0 => all wires. */
+ * n_wires < 0 => all wires.  Above 24 wires (or PLB200_SAMPLES=device) it forwards to the device sampler. */
 int plb200_generate_samples(plb200_sv *sv, const int64_t *wires, int64_t n_wires, int64_t shots,
                             int64_t seed, uint64_t *out);
+/* Measurements::generate_samples (MeasurementsLQubit.hpp:646-679, MeasurementsGPU.hpp generate_samples) with the
+ * table-free device sampler: chunk masses in one sweep, scan, one warp per shot (Philox).  Same distribution and
+ * output layout as plb200_generate_samples, its own random stream; no 2^k host table. */
+int plb200_generate_samples_device(plb200_sv *sv, const int64_t *wires, int64_t n_wires, int64_t shots,
+                                   int64_t seed, uint64_t *out);
 
 /* ------------------------------------------------------------------ adjoint Jacobian
  * AdjointJacobian::adjointJacobian — AdjointJacobianLQubit.hpp:347-491.  jac has

@@ -485,15 +485,19 @@ class StateVector:
     def apply_observable(self, obs: Observable):
         _check(lib().plb200_obs_apply(obs._h, self._h))
 
-    def generate_samples(self, shots, wires=None, seed=-1):
+    def generate_samples(self, shots, wires=None, seed=-1, device=None):
+        """device=None: alias table on the host up to 24 wires (the reference's random stream), the table-free
+        device sampler above; True / False force one of them."""
         if wires is None:
             nw, wp, k = -1, None, self.num_qubits
         else:
             w, wp = _i64(wires)
             nw = k = len(w)
         out = np.empty((shots, k), dtype=np.uint64)
-        _check(lib().plb200_generate_samples(self._h, wp, C.c_int64(nw), C.c_int64(shots), C.c_int64(seed),
-                                             out.ctypes.data_as(_u64p)))
+        fn = lib().plb200_generate_samples_device if device else lib().plb200_generate_samples
+        if device is False and k > 24:
+            raise ValueError("the host alias table is limited to 24 wires")
+        _check(fn(self._h, wp, C.c_int64(nw), C.c_int64(shots), C.c_int64(seed), out.ctypes.data_as(_u64p)))
         return out
 
     def vjp(self, ops, dy, trainable, apply_ops=False):

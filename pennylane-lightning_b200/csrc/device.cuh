@@ -106,6 +106,8 @@ void scale(StateVec &sv, cd alpha);
 void axpy(StateVec &y, cd alpha, const StateVec &x);
 void probs_all(StateVec &sv, double *host_out);
 void probs_wires(StateVec &sv, const std::vector<int> &bits_msb_first, double *host_out);
+// sample_kernels.cu: computational-basis samples drawn on the device; bits[j] = index bit of reported wire j
+void sample_device(StateVec &sv, const std::vector<int> &bits, int64_t shots, uint64_t seed, uint64_t *host_out);
 // sum_i conj(a[i]) (P b)[i] for W words in one launch; out[2*W]
 void pauli_inner(StateVec &a, const StateVec &b, const PauliWordMask *words, int64_t n_words,
                  double *out_re_im);

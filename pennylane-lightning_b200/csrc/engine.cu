@@ -917,8 +917,43 @@ int plb200_var_obs(plb200_sv *sv, const plb200_obs *o, double *out) {
     *out = var_obs(sv->s, *o);
     ABI_CATCH
 }
+int plb200_generate_samples_device(plb200_sv *sv, const int64_t *wires, int64_t nw, int64_t shots, int64_t seed,
+                                   uint64_t *out) {
+    ABI_TRY
+    StateVec &s = sv->s;
+    std::vector<int64_t> w;
+    if (nw < 0) {
+        w.resize(s.n);
+        for (int64_t i = 0; i < s.n; i++) w[i] = i;
+    } else
+        w.assign(wires, wires + nw);
+    PLB_CHECK(!w.empty(), "generate_samples: no wires");
+    uint64_t seen = 0;
+    std::vector<int> bits;
+    for (int64_t x : w) {
+        PLB_CHECK(x >= 0 && x < s.n, "Invalid wire index");
+        PLB_CHECK(!(seen >> x & 1), "Wires must be unique");
+        seen |= uint64_t{1} << x;
+        bits.push_back(static_cast<int>(s.n - 1 - x));
+    }
+    uint64_t sd = static_cast<uint64_t>(seed);
+    if (seed < 0) {
+        std::random_device rd;
+        sd = (static_cast<uint64_t>(rd()) << 32) | rd();
+    }
+    sample_device(s, bits, shots, sd, out);
+    ABI_CATCH
+}
 int plb200_generate_samples(plb200_sv *sv, const int64_t *wires, int64_t nw, int64_t shots, int64_t seed,
                             uint64_t *out) {
+    {
+        // above 24 wires the table no longer belongs on the host (2^k doubles over PCIe, a sequential build):
+        // the device sampler takes over (same distribution, its own random stream); PLB200_SAMPLES=device|alias forces
+        const char *e = std::getenv("PLB200_SAMPLES");
+        const int64_t kk = nw < 0 ? sv->s.n : nw;
+        if ((e && !std::strcmp(e, "device")) || (kk > 24 && !(e && !std::strcmp(e, "alias"))))
+            return plb200_generate_samples_device(sv, wires, nw, shots, seed, out);
+    }
     ABI_TRY
     StateVec &s = sv->s;
     const int64_t k = nw < 0 ? s.n : nw;

@@ -1053,7 +1053,10 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
             refused = false;
             if (k) jit::launch(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream, sv.data, pp);
             else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
-            else if (st.jit_forms) return !(refused = true);
+            else if (st.jit_forms) {
+                refused = true;
+                return false;
+            }
             else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
@@ -1112,8 +1115,10 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
             // A pass in the specialised forms is held only when its plain kernel exists already (it may turn
             // out not to be the last one); otherwise it comes back in the interpreter's forms.
             if (st.jit_forms && jit::mode() != jit::Mode::Sync &&
-                !jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem, false))
-                return !(refused = true);
+                !jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem, false)) {
+                refused = true;
+                return false;
+            }
             std::memcpy(static_cast<void *>(held.get()), pp, sizeof(PassParams<T2>));
             held_st = st, have = true, held_interp = refused;
             refused = false;
@@ -1173,7 +1178,10 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         jit::Kernel k;
         if (use_jit && !refused) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
         refused = false;
-        if (!k && st.jit_forms) return !(refused = true);
+        if (!k && st.jit_forms) {
+            refused = true;
+            return false;
+        }
         if (k) {
             void *a0 = lambda.data, *a1 = hl.data;
             void *args[4] = {&a0, &a1, &pacc, const_cast<PassParams<T2> *>(pp)};

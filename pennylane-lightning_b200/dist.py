@@ -243,6 +243,12 @@ class LocalEngine:
     def host_state(self):
         return self.sv.get_state()
 
+    def sample_bits(self, shots, seed):
+        """`shots` basis states of this slab's (un-normalised) distribution: (shots, nloc) bits, engine wire order"""
+        if shots == 0:
+            return np.zeros((0, self.nloc), dtype=np.uint64)
+        return self.sv.generate_samples(shots, seed=int(seed) & 0x7FFFFFFFFFFFFFFF, device=True)
+
     # ---- linear algebra between slabs with the same layout (sharded adjoint: lambda, H lambda, mu)
     def copy_from(self, other):
         self.sv.copy_from(other.sv)
@@ -701,20 +707,19 @@ class DistStateVector:
         multinomial split on every rank (shared seed, no communication) -> each rank draws its share from its
         slab's distribution -> local bit strings are translated through the wire map and gathered.  (Not the
         reference's alias-table stream: a sharded state has no single table; the distribution is the same.)"""
-        p_loc = np.asarray(self.engine.probs(None), dtype=np.float64)
-        masses = self._allreduce(np.eye(self.world)[self.rank] * p_loc.sum())
+        mass = float(self.engine.pauli_sums(["I"], [[0]])[0])  # this slab's norm^2
+        masses = self._allreduce(np.eye(self.world)[self.rank] * mass)
         masses = masses / masses.sum()
         counts = np.random.default_rng(seed).multinomial(shots, masses)
         mine = int(counts[self.rank])
-        rng = np.random.default_rng([seed, self.rank])
-        cdf = np.cumsum(p_loc)
-        draws = np.searchsorted(cdf, rng.random(mine) * cdf[-1], side="right").clip(0, len(cdf) - 1)
+        # the slab is sampled where it lives (LocalEngine: the table-free device sampler, no 2^nloc host table)
+        local = self.engine.sample_bits(mine, seed * 1000003 + self.rank)  # (mine, nloc), engine wire order
         bits = np.zeros((mine, self.n), dtype=np.uint64)
         for w in range(self.n):
             if self._is_global(w):
                 bits[:, w] = self._rank_bit(w)
             else:
-                bits[:, w] = (draws >> self.phys[w]) & 1
+                bits[:, w] = local[:, self._lw(w)]
         parts = [None] * self.world
         self.dist.all_gather_object(parts, bits, group=self.group)
         return np.concatenate(parts, axis=0)

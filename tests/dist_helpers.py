@@ -63,6 +63,12 @@ class NumpyEngine:
     def host_state(self):
         return self.sv.state.copy()
 
+    def sample_bits(self, shots, seed):
+        p = np.abs(self.sv.state.astype(np.complex128)) ** 2
+        cdf = np.cumsum(p)
+        draws = np.searchsorted(cdf, np.random.default_rng(seed).random(shots) * cdf[-1], side="right").clip(0, len(cdf) - 1)
+        return np.stack([(draws >> (self.nloc - 1 - w)) & 1 for w in range(self.nloc)], axis=1).astype(np.uint64).reshape(shots, self.nloc)
+
     def copy_from(self, other):
         self.sv.state[:] = other.sv.state
 

@@ -201,6 +201,49 @@ def test_samples_bit_exact(plb, ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [3, 10, 15])
+def test_device_sampler_distribution(plb, dtype, n):
+    """plb200_generate_samples_device (chunk masses -> scan -> one warp per shot): same distribution as the exact
+    probabilities (total-variation distance and per-wire marginals within sampling error), reproducible under a
+    seed, different under another, wire subsets in the caller's order, sparse states never yield a zero-probability
+    outcome."""
+    ops = circuits.random_circuit(n, 3, 5)
+    a = plb.StateVector(n, dtype)
+    a.apply_ops(ops, fuse=False)
+    shots = 200000
+    s = a.generate_samples(shots, seed=3, device=True)
+    assert s.shape == (shots, n) and s.dtype == np.uint64 and set(np.unique(s)) <= {0, 1}
+    np.testing.assert_array_equal(s, a.generate_samples(shots, seed=3, device=True))
+    assert not np.array_equal(s, a.generate_samples(shots, seed=4, device=True))
+    p = np.asarray(a.probs(), dtype=np.float64)
+    idx = (s * (1 << np.arange(n - 1, -1, -1, dtype=np.uint64))).sum(axis=1).astype(np.int64)
+    emp = np.bincount(idx, minlength=2**n) / shots
+    # E[TV] ~ sqrt(K / (2 pi shots)) for K outcomes: 0.16 at K = 2^15; three times that is a wrong distribution
+    assert 0.5 * np.abs(emp - p).sum() < 0.02 + 1.5 * np.sqrt(2.0**n / (2 * np.pi * shots))
+    for w in range(n):
+        exact = a.expval_pauli_words_each(["Z"], [[w]])[0]
+        assert abs((1.0 - 2.0 * s[:, w].mean()) - exact) < 5.0 / np.sqrt(shots)
+    # a wire subset in a scrambled order = the marginal, columns in that order
+    sub = [n - 1, 0, n // 2] if n >= 3 else [0]
+    t = a.generate_samples(shots, wires=sub, seed=9, device=True)
+    assert t.shape == (shots, len(sub))
+    pm = np.asarray(a.probs(sub))
+    ti = (t * (1 << np.arange(len(sub) - 1, -1, -1, dtype=np.uint64))).sum(axis=1).astype(np.int64)
+    assert np.max(np.abs(np.bincount(ti, minlength=2 ** len(sub)) / shots - pm)) < 5.0 / np.sqrt(shots)
+    # a sparse state: only outcomes with non-zero probability may appear
+    b = plb.StateVector(n, dtype)
+    amp = np.zeros(2**n, dtype=dtype)
+    support = [0, 2**n - 1, 5 % 2**n]
+    amp[support] = [0.6, 0.0, 0.8] if len(set(support)) == 3 else 1.0
+    amp[support[1]] = 0.0
+    amp /= np.linalg.norm(amp)
+    b.set_state(amp)
+    u = b.generate_samples(5000, seed=1, device=True)
+    ui = (u * (1 << np.arange(n - 1, -1, -1, dtype=np.uint64))).sum(axis=1).astype(np.int64)
+    assert set(np.unique(ui)) <= {i for i in support if abs(amp[i]) > 0}
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_linear_algebra(plb, dtype):
     n = 10
     x, y = random_state(n, dtype, 1), random_state(n, dtype, 2)
