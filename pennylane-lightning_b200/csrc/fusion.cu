@@ -990,6 +990,18 @@ template <typename T2> jit::Route tile_route(const RouteSpec &rs, const PassPara
         rp.opos[i] = static_cast<uint32_t>(rs.lbits[i]);
     }
     for (int p = 0; p < (1 << rs.k); p++) rp.dst[p] = static_cast<T2 *>(rs.dst[p]);
+    // tile-index positions of the swapped bits outside the tile (index bit minus the tile bits below it), ascending
+    std::vector<uint32_t> tq;
+    for (int i = 0; i < rs.k; i++) {
+        if (r.loc[i] >= 0) continue;
+        uint32_t below = 0;
+        for (int b = 0; b < pp.hdr.tile_ins.n; b++)
+            if (pp.hdr.tile_ins.lowmask[b] + 1 < (uint64_t{1} << rs.lbits[i])) below++;
+        tq.push_back(static_cast<uint32_t>(rs.lbits[i]) - below);
+    }
+    std::sort(tq.begin(), tq.end());
+    rp.ntq = static_cast<uint32_t>(tq.size());
+    for (size_t i = 0; i < tq.size(); i++) rp.tq[i] = tq[i];
     return r;
 }
 

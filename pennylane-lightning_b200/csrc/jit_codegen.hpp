@@ -76,7 +76,21 @@ struct PLB_ALIGN(16) LadderEntry { u64 cmask_o; u32 cm_tid, pad; T2 ph; };
 struct PLB_ALIGN(16) RoundHdr { int first_op, nops, nlad, pad; u32 w[9]; u32 sroff[32]; };
 struct PLB_ALIGN(16) PassHdr { int nrounds, nops_total; u64 ntiles; int nslots, pad; BitInsert tile_ins; };
 struct PLB_ALIGN(16) PassParams { PassHdr hdr; RoundHdr rounds[PLB_MAXROUNDS]; TileOp ops[PLB_MAXOPS + 1]; };
-struct PLB_ALIGN(16) RouteParams { T2 *dst[8]; u64 lmask, rdep; u32 opos[4]; };
+struct PLB_ALIGN(16) RouteParams { T2 *dst[8]; u64 lmask, rdep; u32 opos[4]; u32 tq[3]; u32 ntq; };
+// Order in which a routed pass walks its tiles.  A swapped bit that lies OUTSIDE the tile selects the destination
+// slab per tile; walking the tiles in index order would send to one peer for a long stretch (first all of the
+// pass's stores stay local, then all of them cross NVLink to ONE peer, and every rank picks the same peer at the
+// same time).  The loop counter's low bits are therefore placed at those tile-index positions: consecutive CTAs
+// — the ones resident together — target all 2^k destinations evenly, for the whole duration of the pass.
+DEV u64 route_tile(u64 c, const RouteParams &rp) {
+    const u32 k = rp.ntq;
+    u64 t = c >> k;
+    for (u32 i = 0; i < k; i++) { // tq ascending: insert bit i of the counter at tile-index position tq[i]
+        const u64 m = (1ull << rp.tq[i]) - 1ull;
+        t = ((t & ~m) << 1) | (t & m) | (((c >> i) & 1ull) << rp.tq[i]);
+    }
+    return t;
+}
 static_assert(sizeof(TileOp) == PLB_SIZEOF_TILEOP, "TileOp layout");
 static_assert(sizeof(PassParams) == PLB_SIZEOF_PASSPARAMS, "PassParams layout");
 static_assert(sizeof(PassHdr) + PLB_MAXROUNDS * sizeof(RoundHdr) == PLB_OFFSETOF_OPS, "PassParams layout");
@@ -274,6 +288,8 @@ template <typename T2> struct alignas(16) RouteParams {
     uint64_t lmask;    // the swapped local bits, as a mask over the slab index
     uint64_t rdep;     // this rank's values of the swapped global bits, deposited at those positions
     uint32_t opos[4];  // index-bit position of swapped bit i (used when it lies outside the tile)
+    uint32_t tq[3];    // tile-index positions of the swapped bits outside the tile, ascending (route_tile)
+    uint32_t ntq;
 };
 
 template <typename T2, class Cfg> class Gen {
@@ -908,7 +924,7 @@ template <typename T2, class Cfg> class Gen {
              "    static u64 goff[1 << (PLB_M - PLB_LOW)];\n"
              "    for (int i = 0; i < (1 << (PLB_M - PLB_LOW)); i++) goff[i] = tile_line_offset(pp.hdr, i);\n"
              "    for (u64 t = 0; t < pp.hdr.ntiles; t++) {\n"
-             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n" +
+             "        const u64 base = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t, rp)" : "t") + ", pp.hdr.tile_ins);\n" +
              host +
              "    }\n}\n"
              "#else\n"
@@ -921,9 +937,9 @@ template <typename T2, class Cfg> class Gen {
              "    __syncthreads();\n"
              "    const u32 tid = threadIdx.x;\n"
              "    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {\n"
-             "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n"
+             "        const u64 base = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t, rp)" : "t") + ", pp.hdr.tile_ins);\n"
              "        if (t + gridDim.x < pp.hdr.ntiles) {\n"
-             "            const u64 nbase = insert_bits_m(t + gridDim.x, pp.hdr.tile_ins);\n"
+             "            const u64 nbase = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t + gridDim.x, rp)" : "t + gridDim.x") + ", pp.hdr.tile_ins);\n"
              "            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT)\n"
              "                asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(sv + (nbase | goff[l])));\n"
              "        }\n" +

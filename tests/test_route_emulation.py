@@ -46,6 +46,10 @@ def _tape(kind, nloc):
     (np.complex128, 2, 13, [10, 3], "tail"),
     (np.complex128, 1, 13, [6], "one"),
     (np.complex128, 2, 13, [12, 8], "empty"),
+    # swapped bits OUTSIDE the tile, unsorted: the tile walk is permuted (route_tile) so that consecutive tiles hit
+    # every destination; every tile must still be visited exactly once
+    (np.complex128, 3, 15, [14, 12, 13], "empty"),
+    (np.complex128, 3, 15, [13, 11, 14], "random"),
 ])
 def test_routed_pass_equals_apply_then_swap(emu, plb, dtype, g, nloc, lbits, kind, monkeypatch):
     monkeypatch.setenv("PLB200_EMU_JIT", "1")
