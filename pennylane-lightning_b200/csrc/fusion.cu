@@ -223,7 +223,15 @@ bool is_pair2(const COp &op) {
     return true;
 }
 
-FOp classify(const COp &op, bool pair2 = false) {
+// DoubleExcitation-like: one or two 2x2 blocks on a 4-bit target space (K_PAIR4, needs 4 register bits)
+bool is_pair4(const COp &op) {
+    if (op.kind != OP_PAIRS || op.parity || op.tbits.size() != 4 || op.blocks.empty() || op.blocks.size() > 2) return false;
+    for (const Block2 &b : op.blocks)
+        if (b.a > 15 || b.b > 15 || b.a == b.b || !well_conditioned(b.m)) return false;
+    return true;
+}
+
+FOp classify(const COp &op, bool pair2 = false, int reg_bits = 4) {
     FOp f;
     uint64_t t = 0;
     for (int b : op.tbits) t |= uint64_t{1} << b;
@@ -236,7 +244,7 @@ FOp classify(const COp &op, bool pair2 = false) {
     } else if (is_swap2(op)) {
         f.fusable = true;
         f.nd = t;
-    } else if (pair2 && is_pair2(op)) {
+    } else if (pair2 && (is_pair2(op) || (reg_bits >= 4 && is_pair4(op)))) {
         f.fusable = true;
         f.nd = t;
     } else if (op.kind == OP_DIAG) {
@@ -255,8 +263,8 @@ FOp classify(const COp &op, bool pair2 = false) {
     return f;
 }
 
-FOp classify(const AdjItem &it, bool pair2 = false) {
-    if (!it.overlap) return classify(it.op, pair2);
+FOp classify(const AdjItem &it, bool pair2 = false, int reg_bits = 4) {
+    if (!it.overlap) return classify(it.op, pair2, reg_bits);
     FOp f;
     const PauliWordMask &w = it.pw;
     f.nd = w.x;
@@ -451,7 +459,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
     std::vector<FOp> f(items.size());
     const bool pair2 = Cfg::NS == 1 && pair2_enabled();
     for (size_t i = 0; i < items.size(); i++) {
-        f[i] = classify(items[i], pair2);
+        f[i] = classify(items[i], pair2, R);
         f[i].all &= full;
     }
     std::vector<char> done(items.size(), 0);
@@ -508,8 +516,8 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             size_t emitted = 0, keep = 0;
             for (int i : exec) {
                 const AdjItem &it = items[i];
-                if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() == 2 && !is_swap2(it.op))
-                    emitted += 2 * it.op.blocks.size(); // K_PAIR2: one record per block (+ a pivot each at most)
+                if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op))
+                    emitted += 2 * it.op.blocks.size(); // K_PAIR2 / K_PAIR4: one record per block (+ a pivot each at most)
                 else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG && it.op.cmask != 0 &&
                          __builtin_popcountll(f[i].pmask) == 1 && f[i].d[0] != cd(1.0))
                     emitted += 2; // a controlled two-valued diagonal may split into two controlled phases
@@ -714,24 +722,33 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 } else if (is_swap2(it.op)) {
                     st.ext = true;
                     t.code = make_code(cm_reg ? K_SWAP2_M : K_SWAP2, reg_pos(it.op.tbits[0]), reg_pos(it.op.tbits[1]));
-                } else if (it.op.kind == OP_PAIRS && it.op.tbits.size() == 2) {
-                    // two-bit pair op: one K_PAIR2 record per 2x2 block (a pivot X on the pair first when needed)
+                } else if (it.op.kind == OP_PAIRS && (it.op.tbits.size() == 2 || it.op.tbits.size() == 4)) {
+                    // two- / four-bit pair op: one K_PAIR2 / K_PAIR4 record per 2x2 block (a pivot X on the pair first
+                    // when needed)
                     st.jit_only = true;
+                    const bool four = it.op.tbits.size() == 4;
                     const int p = reg_pos(it.op.tbits[0]), c = reg_pos(it.op.tbits[1]);
-                    t.code = make_code(K_PAIR2, p, c);
+                    uint32_t pos4 = 0;
+                    if (four)
+                        for (int j = 0; j < 4; j++) pos4 |= static_cast<uint32_t>(reg_pos(it.op.tbits[j])) << (12 + 3 * j);
+                    t.code = make_code(four ? K_PAIR4 : K_PAIR2, four ? 0 : p, four ? 0 : c);
                     if (t.cm_tid | t.cmask_o) t.code |= F_COND;
+                    auto pack = [&](const Block2 &bl, int form) {
+                        return four ? (bl.a | (bl.b << 4) | (static_cast<uint32_t>(form) << 8) | pos4)
+                                    : (bl.a | (bl.b << 2) | (static_cast<uint32_t>(form) << 4));
+                    };
                     for (const Block2 &bl : it.op.blocks) {
                         const PairForm pf = pair_form(bl.m, false);
                         TileOp<T2> rec = t;
                         if (pf.pre_swap) {
                             TileOp<T2> x = t;
-                            x.slot = bl.a | (bl.b << 2) | (static_cast<uint32_t>(K_SWAP) << 4);
+                            x.slot = pack(bl, K_SWAP);
                             top[op_cursor++] = x;
                         }
-                        rec.slot = bl.a | (bl.b << 2) | (static_cast<uint32_t>(pf.kind) << 4);
+                        rec.slot = pack(bl, pf.kind);
                         for (int q = 0; q < 4; q++) rec.m[q] = mk<T2>(pf.m[q].real(), pf.m[q].imag());
 #if defined(PLB200_HOST_EMU)
-                        g_kind_hist[K_PAIR2]++;
+                        g_kind_hist[four ? K_PAIR4 : K_PAIR2]++;
 #endif
                         top[op_cursor++] = rec;
                     }

@@ -654,13 +654,24 @@ template <typename T2, class Cfg> class Gen {
                 close_cond();
             }
         } break;
-        case K_PAIR2: { // one 2x2 block of a two-bit pair op on the registers with (C, P) = a and = b
-            const unsigned a2 = op.slot & 3u, b2 = (op.slot >> 2) & 3u;
-            const int form = static_cast<int>((op.slot >> 4) & 15u);
-            auto dep = [&](unsigned x) { return static_cast<int>(((x & 1u) << P) | ((x >> 1) << C)); };
+        case K_PAIR2: case K_PAIR4: { // one 2x2 block of a two- / four-bit pair op on the registers whose target bits = a and = b
+            const bool four = kind == K_PAIR4;
+            const unsigned a2 = four ? (op.slot & 15u) : (op.slot & 3u), b2 = four ? ((op.slot >> 4) & 15u) : ((op.slot >> 2) & 3u);
+            const int form = static_cast<int>((op.slot >> (four ? 8 : 4)) & 15u);
+            int pos[4] = {P, C, 0, 0};
+            if (four)
+                for (int j = 0; j < 4; j++) pos[j] = static_cast<int>((op.slot >> (12 + 3 * j)) & 7u);
+            const int nb = four ? 4 : 2;
+            int tmask = 0;
+            for (int j = 0; j < nb; j++) tmask |= 1 << pos[j];
+            auto dep = [&](unsigned x) {
+                int r = 0;
+                for (int j = 0; j < nb; j++) r |= static_cast<int>((x >> j) & 1u) << pos[j];
+                return r;
+            };
             pr.clear();
             for (int u = 0; u < NV; u++) {
-                if (((u >> P) & 1) || ((u >> C) & 1)) continue;
+                if (u & tmask) continue;
                 const int ua = u | dep(a2), ub = u | dep(b2);
                 if (!((op.umask >> ua) & 1u)) continue;
                 pr.emplace_back(ua, ub);

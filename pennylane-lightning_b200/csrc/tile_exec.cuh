@@ -142,6 +142,11 @@ enum : int {
     K_SROT_I = 28,
     K_SROK_R = 29,
     K_SROK_I = 30,
+    // One 2x2 block of a FOUR-bit pair op (DoubleExcitation: a Givens rotation on |0011>, |1100>): all four target
+    // bits are register bits of the round; slot = a | b << 4 | form << 8 | pos0 << 12 | pos1 << 15 | pos2 << 18 |
+    // pos3 << 21 (a, b: 4-bit values over the target bits, pos_j: register bit carrying target bit j).  Specialised
+    // kernels only, like K_PAIR2.
+    K_PAIR4 = 31,
     K_LAST_OVL = K_OVL_D,
     K_FIRST_DIAG = K_DIAG_R,
     K_FIRST_OVL = K_OVL_X,

@@ -92,7 +92,12 @@ def _pair2_tape(n, seed, count=120):
               "CNOT", "IsingZZ"]
     ops = []
     for _ in range(count):
-        if rng.random() < 0.45:
+        if rng.random() < 0.12:  # four-bit pair op (K_PAIR4): a Givens rotation on |0011>, |1100>, also controlled
+            w = [int(x) for x in rng.permutation(n)[:5]]
+            ctrl = w[4:5] if rng.random() < 0.3 else []
+            ops.append(circuits.op("DoubleExcitation", w[:4], [rng.uniform(0, 6)], inverse=bool(rng.integers(2)),
+                                   ctrl_wires=ctrl, ctrl_values=[bool(rng.integers(2))] * len(ctrl)))
+        elif rng.random() < 0.45:
             ops.append(circuits.op(("RX", "RY", "RZ", "Hadamard")[int(rng.integers(4))], [int(rng.integers(n))],
                                    [rng.uniform(0, 6)] if rng.random() < 2 else []))
             if ops[-1]["name"] == "Hadamard":
@@ -109,7 +114,8 @@ def _pair2_tape(n, seed, count=120):
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 def test_two_bit_pair_ops_fused_on_host(plb, dtype, monkeypatch):
     """PLB200_FUSE_PAIR2=1: IsingXX / XY / YY, SingleExcitation(+-), PSWAP (also controlled) run INSIDE the tile
-    passes as K_PAIR2 ops of the generated code: no stand-alone kernels, oracle's amplitudes."""
+    passes as K_PAIR2 ops of the generated code, DoubleExcitation as K_PAIR4: no stand-alone kernels, oracle's
+    amplitudes."""
     import subprocess
 
     from test_tile_emulation import CSRC, EMU, emu_apply, oracle_apply
@@ -128,7 +134,7 @@ def test_two_bit_pair_ops_fused_on_host(plb, dtype, monkeypatch):
     np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=TOL[np.dtype(dtype)])
     hist = (C.c_int64 * 32)()
     emu.plb200_emu_kind_histogram(hist, 1)
-    assert hist[26] > 0  # K_PAIR2 records were emitted
+    assert hist[26] > 0 and hist[31] > 0  # K_PAIR2 and K_PAIR4 records were emitted
     # without the switch the same tape leaves those gates stand-alone
     monkeypatch.setenv("PLB200_FUSE_PAIR2", "0")
     _, stats0 = emu_apply(emu, plb, n, ops, st, True)
@@ -380,3 +386,31 @@ def test_pass_sources_do_not_depend_on_angles_or_on_refusals(plb, prec, monkeypa
     assert sources(ops, "b", True) == a
     assert sources(ops2, "c", False) == a
     assert sources(ops2, "d", True) == a
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_jit_forms_special_angles_on_device(plb, ref, jit_sync, dtype):
+    """Scaled rotations on the device: half turns (cotangent form), angles a hair away from them (tangents up to
+    2^16, growth bounded per pass), zero angles, mixed with CRZ / CNOT / controlled phases (split diagonals,
+    in-stream ladders) — against lightning.qubit."""
+    n = 20
+    rng = np.random.default_rng(23)
+    special = [np.pi, -np.pi, 3 * np.pi, np.pi - 1e-6, np.pi + 1e-4, 0.0, 2 * np.pi, np.pi / 2]
+    ops = []
+    for layer in range(6):
+        for w in range(n):
+            th = special[int(rng.integers(len(special)))] if rng.random() < 0.4 else rng.uniform(0, 2 * np.pi)
+            ops.append(circuits.op(("RX", "RY", "RZ")[int(rng.integers(3))], [w], [th], inverse=bool(rng.integers(2))))
+        p = rng.permutation(n)
+        for i in range(0, n - 1, 2):
+            nm = ("CNOT", "CRZ", "ControlledPhaseShift", "CZ")[int(rng.integers(4))]
+            ops.append(circuits.op(nm, [int(p[i]), int(p[i + 1])], [rng.uniform(0, 6)] if nm in ("CRZ", "ControlledPhaseShift") else []))
+    s0 = plb.jit_stats()
+    a = plb.StateVector(n, dtype)
+    a.apply_ops(ops, fuse=True)
+    s1 = plb.jit_stats()
+    assert s1["jit_launches"] > s0["jit_launches"]
+    r = ref.StateVector(n, dtype)
+    r.apply_ops(ops)
+    np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=4 * TOL[np.dtype(dtype)])
