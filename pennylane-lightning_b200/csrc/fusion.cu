@@ -206,14 +206,17 @@ bool is_swap2(const COp &op) {
            b.m[1] == cd(1.0) && b.m[2] == cd(1.0);
 }
 
-// Two-bit pair ops inside tile passes (K_PAIR2).  They need a specialised kernel, compiled at first sight, so
-// they are fused only when that is the regime the user chose: PLB200_JIT=sync, or PLB200_FUSE_PAIR2=1.
-bool pair2_enabled() {
+// Two- / four-bit pair ops inside tile passes (K_PAIR2 / K_PAIR4).  They need a specialised kernel; PLB200_FUSE_PAIR2
+// forces the choice.
+bool pair2_enabled(int n) {
     if (const char *e = std::getenv("PLB200_FUSE_PAIR2")) return e[0] != '0';
 #if defined(PLB200_HOST_EMU)
+    (void)n;
     return false;
 #else
-    return jit::mode() == jit::Mode::Sync && jit::available(nullptr);
+    // whenever specialised kernels are in play: compiled at first sight (PLB200_JIT=sync), or in the background
+    // (default tier) — until a pass's kernel exists the pass is cut at its pair ops (build_schedule)
+    return jit::mode() != jit::Mode::Off && jit::available(nullptr) && n >= jit::min_qubits();
 #endif
 }
 bool is_pair2(const COp &op) {
@@ -347,6 +350,7 @@ struct Step {
     int nrounds = 0, nops = 0;
     bool ext = false; // needs the extended kernel (two-bit SWAPs / tail ladders)
     bool jit_only = false; // holds K_PAIR2 ops: only a specialised kernel can run it
+    bool fallback = false;  // the interpreter's encoding of (a piece of) a pass the consumer refused: no kernel to look for
     bool jit_forms = false; // encoded with forms only the specialised kernels have (scaled rotations, in-stream
                             // ladders); a consumer that cannot run it says so and gets the interpreter encoding
     std::vector<int> slots;          // adjoint: global accumulator slot of each pass-local slot
@@ -457,7 +461,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                             ((sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr);
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
     std::vector<FOp> f(items.size());
-    const bool pair2 = Cfg::NS == 1 && pair2_enabled();
+    const bool pair2 = Cfg::NS == 1 && pair2_enabled(n);
     for (size_t i = 0; i < items.size(); i++) {
         f[i] = classify(items[i], pair2, R);
         f[i].all &= full;
@@ -557,35 +561,35 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         for (const auto &r : hp.rounds) pass_ops.insert(pass_ops.end(), r.begin(), r.end());
         for (int i : pass_ops) done[i] = 1;
         // the last step of the tape?  (then the carried scalar is multiplied back here)
-        bool tape_done = true;
-        for (size_t i = first; i < items.size() && tape_done; i++) tape_done = done[i] != 0;
+        bool tape_ends = true;
+        for (size_t i = first; i < items.size() && tape_ends; i++) tape_ends = done[i] != 0;
 
         // ---- encode the plan (jf: in the forms of the specialised kernels)
-        auto encode = [&](const bool jf) -> Step {
+        auto encode = [&](const bool jf, const HostPass &hq, const bool tape_done) -> Step {
         std::memset(static_cast<void *>(cur.get()), 0, sizeof(PassParams<T2>));
         PassHdr *hdr = &cur->hdr;
         RoundHdr *rh = cur->rounds;
         TileOp<T2> *top = cur->ops;
-        hdr->nrounds = static_cast<int>(hp.rounds.size());
+        hdr->nrounds = static_cast<int>(hq.rounds.size());
         hdr->ntiles = uint64_t{1} << (n - M);
         hdr->tile_ins.n = 0;
-        for (int b : hp.tbits) hdr->tile_ins.lowmask[hdr->tile_ins.n++] = (uint64_t{1} << b) - 1;
+        for (int b : hq.tbits) hdr->tile_ins.lowmask[hdr->tile_ins.n++] = (uint64_t{1} << b) - 1;
         int local_of[64];
         for (int i = 0; i < 64; i++) local_of[i] = -1;
-        for (int i = 0; i < M; i++) local_of[hp.tbits[i]] = i;
+        for (int i = 0; i < M; i++) local_of[hq.tbits[i]] = i;
         auto to_local = [&](uint64_t mask) {
             uint32_t l = 0;
             for (int i = 0; i < M; i++)
-                if (mask >> hp.tbits[i] & 1) l |= 1u << i;
+                if (mask >> hq.tbits[i] & 1) l |= 1u << i;
             return l;
         };
         Step st;
         int op_cursor = 0;
         double pass_growth = 1.0; // growth of the stored amplitudes by this pass's scaled rotations
-        for (size_t r = 0; r < hp.rounds.size(); r++) {
+        for (size_t r = 0; r < hq.rounds.size(); r++) {
             std::vector<int> rl; // local positions of the register bits, ascending
             for (int i = 0; i < M; i++)
-                if (hp.round_bits[r] >> hp.tbits[i] & 1) rl.push_back(i);
+                if (hq.round_bits[r] >> hq.tbits[i] & 1) rl.push_back(i);
             uint32_t rmask_l = 0;
             for (int i = 0; i < R; i++) rmask_l |= 1u << rl[i];
             // ---- thread-bit assignment.  Low SB lane bits: tile bits with independent swizzle
@@ -593,7 +597,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             // uses as a control / parity bit; the most used ones end up in the warp-index bits, so
             // conditional ops diverge as little as possible.
             int use[32] = {0};
-            for (int idx : hp.rounds[r]) {
+            for (int idx : hq.rounds[r]) {
                 const AdjItem &it = items[idx];
                 const uint64_t cm = it.overlap ? it.pw.cmask : it.op.cmask;
                 const uint64_t pm = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : f[idx].pmask);
@@ -616,7 +620,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 // a specialised kernel (jit_codegen.hpp) moves that round's registers straight from / to
                 // global memory.
                 static_assert(SB == LOW, "the contiguous tile bits are the bank-group bits");
-                const bool edge_round = (r == 0 || r + 1 == hp.rounds.size()) && Cfg::NS == 1;
+                const bool edge_round = (r == 0 || r + 1 == hq.rounds.size()) && Cfg::NS == 1;
                 if (edge_round && (rmask_l & ((1u << LOW) - 1u)) == 0) {
                     for (int i = 0; i < LOW; i++) {
                         tpos.push_back(i), taken[i] = 1;
@@ -683,7 +687,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                         if (ones) {
                             uint64_t pick = 0;
                             for (int i = 0; i < R && !pick; i++)
-                                if (ones >> hp.tbits[rl[i]] & 1) pick = uint64_t{1} << hp.tbits[rl[i]];
+                                if (ones >> hq.tbits[rl[i]] & 1) pick = uint64_t{1} << hq.tbits[rl[i]];
                             if (!pick && (ones & T)) pick = uint64_t{1} << __builtin_ctzll(ones & T);
                             if (!pick) pick = uint64_t{1} << __builtin_ctzll(ones);
                             pmask = pick, cmask &= ~pick, cval &= ~pick;
@@ -895,7 +899,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 }
                 bucket[bk].clear();
             };
-            for (int idx : hp.rounds[r]) {
+            for (int idx : hq.rounds[r]) {
                 const AdjItem &it = items[idx];
                 LEntry e[2];
                 if (const int ne = ladder_entries(idx, e)) {
@@ -911,7 +915,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 else if (it.op.kind == OP_PAIRS)
                     for (int b : it.op.tbits) ndbits |= uint64_t{1} << b;
                 for (int i = 0; i < R; i++)
-                    if (ndbits >> hp.tbits[rl[i]] & 1) flush_bucket(i);
+                    if (ndbits >> hq.tbits[rl[i]] & 1) flush_bucket(i);
                 emit_item(idx);
             }
             for (int bk = 0; bk <= R; bk++)
@@ -920,7 +924,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             // there (adjoint passes, the end of the tape, |sigma| about to leave its range) or not (the slot then
             // holds 1 and the specialised kernels skip it): the structure of a pass — the key of its compiled
             // kernel — must not depend on the angles of the passes before it.
-            if (r + 1 == hp.rounds.size()) {
+            if (r + 1 == hq.rounds.size()) {
                 const double mag = std::abs(sigma);
                 const bool fold = sigma != cd(1.0) && (Cfg::NS == 2 || tape_done || mag < sig_lo || mag > sig_hi);
                 top[op_cursor++] = scale_op(fold ? sigma : cd(1.0));
@@ -938,7 +942,8 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         hdr->nops_total = op_cursor;
         hdr->nslots = static_cast<int>(st.slots.size());
         st.grid = static_cast<unsigned>(std::min<uint64_t>(hdr->ntiles, uint64_t(sm_count) * 3 * 64));
-        st.nrounds = hdr->nrounds, st.nops = static_cast<int>(pass_ops.size());
+        st.nrounds = hdr->nrounds, st.nops = 0;
+        for (const auto &rr : hq.rounds) st.nops += static_cast<int>(rr.size());
         return st;
         }; // encode
         auto deliver = [&](const Step &st) {
@@ -949,12 +954,48 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             }
         };
         const cd sigma_in = sigma;
-        Step st = encode(jit_forms);
+        Step st = encode(jit_forms, hp, tape_ends);
         if (!deliver(st)) {
-            if (!st.jit_forms) fail("fusion: a pass in the interpreter's forms was refused");
+            if (!st.jit_forms && !st.jit_only) fail("fusion: a pass in the interpreter's forms was refused");
             sigma = sigma_in;
-            st = encode(false);
-            if (!deliver(st)) fail("fusion: a pass in the interpreter's forms was refused");
+            if (!st.jit_only) {
+                st = encode(false, hp, tape_ends);
+                st.fallback = true;
+                if (!deliver(st)) fail("fusion: a pass in the interpreter's forms was refused");
+            } else {
+                // The pass holds two- / four-bit pair ops, which only a specialised kernel can run inside a tile, and
+                // that kernel does not exist yet: the pass is cut at those ops — what lies between them runs as
+                // interpreter passes over the same tile (same rounds, same order), the pair ops stand-alone.
+                HostPass piece;
+                piece.tbits = hp.tbits;
+                auto flush_piece = [&](bool last) {
+                    if (piece.rounds.empty()) return;
+                    Step sp = encode(false, piece, last && tape_ends);
+                    sp.fallback = true;
+                    if (sp.jit_only || !deliver(sp)) fail("fusion: a pass in the interpreter's forms was refused");
+                    piece.rounds.clear(), piece.round_bits.clear();
+                };
+                auto needs_kernel = [&](int idx) {
+                    const AdjItem &it = items[idx];
+                    return !it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op);
+                };
+                for (size_t r = 0; r < hp.rounds.size(); r++) {
+                    std::vector<int> run;
+                    for (int idx : hp.rounds[r]) {
+                        if (!needs_kernel(idx)) {
+                            run.push_back(idx);
+                            continue;
+                        }
+                        if (!run.empty()) piece.rounds.push_back(run), piece.round_bits.push_back(hp.round_bits[r]), run.clear();
+                        flush_piece(false);
+                        Step so;
+                        so.op = idx;
+                        on_step(so, nullptr);
+                    }
+                    if (!run.empty()) piece.rounds.push_back(run), piece.round_bits.push_back(hp.round_bits[r]);
+                }
+                flush_piece(true); // (a scalar left when the pass ends with a pair op is folded by a later slot / the final sweep)
+            }
         }
     }
     if (sigma != cd(1.0)) {
@@ -1068,7 +1109,6 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         PLB_CUDA(cudaEventCreate(&ev0));
         PLB_CUDA(cudaEventCreate(&ev1));
     }
-    bool refused = false; // the pass at hand came back in the interpreter's forms: its kernel is not there yet
     build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
@@ -1077,15 +1117,10 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         else {
             // the pass's specialised kernel when the cache has it (jit_runtime.cpp), else the interpreter
             jit::Kernel k;
-            if ((use_jit && !refused) || st.jit_only)
-                k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>(), st.jit_only);
-            refused = false;
+            if ((use_jit && !st.fallback) || st.jit_only)
+                k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem_bytes_for<Cfg, T2>(), false);
             if (k) jit::launch(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), sv.stream, sv.data, pp);
-            else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
-            else if (st.jit_forms) {
-                refused = true;
-                return false;
-            }
+            else if (st.jit_forms || st.jit_only) return false; // no kernel (yet): the interpreter's encoding, please
             else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, *pp);
             sv.launches++;
         }
@@ -1124,17 +1159,15 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
     auto held = std::make_unique<PassParams<T2>>();
     Step held_st;
     bool have = false;
-    bool held_interp = false; // the held pass is the interpreter's encoding of a refused pass: no kernel to look for
     auto launch_plain = [&](const Step &st, const PassParams<T2> &pp) {
         jit::Kernel k;
-        if ((use_jit && !held_interp) || st.jit_only)
+        if ((use_jit && !st.fallback) || st.jit_only)
             k = jit::lookup(jit::generate_pass_source<T2, Cfg>(pp), sv.device, smem, st.jit_only || st.jit_forms);
         if (k) jit::launch(k, st.grid, nt, smem, sv.stream, sv.data, &pp);
         else if (st.jit_only) fail("a pass with two-bit pair ops needs its specialised kernel (NVRTC compile failed)");
         else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, pp);
         sv.launches++;
     };
-    bool refused = false;
     build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (have) launch_plain(held_st, *held), have = false; // the held pass was not the last step
@@ -1143,14 +1176,11 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
         else {
             // A pass in the specialised forms is held only when its plain kernel exists already (it may turn
             // out not to be the last one); otherwise it comes back in the interpreter's forms.
-            if (st.jit_forms && jit::mode() != jit::Mode::Sync &&
-                !jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem, false)) {
-                refused = true;
+            if ((st.jit_forms || st.jit_only) && jit::mode() != jit::Mode::Sync &&
+                !jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), sv.device, smem, false))
                 return false;
-            }
             std::memcpy(static_cast<void *>(held.get()), pp, sizeof(PassParams<T2>));
-            held_st = st, have = true, held_interp = refused;
-            refused = false;
+            held_st = st, have = true;
         }
         return true;
     });
@@ -1186,7 +1216,6 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         std::vector<double> scale;
     };
     std::vector<PassSlots> passes;
-    bool refused = false;
     build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (st.op >= 0) {
@@ -1205,12 +1234,8 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         if (st.op == -2) fail("fusion: adjoint passes carry no scalar across passes");
         double *pacc = dacc + passes.size() * kMaxPassOps;
         jit::Kernel k;
-        if (use_jit && !refused) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
-        refused = false;
-        if (!k && st.jit_forms) {
-            refused = true;
-            return false;
-        }
+        if (use_jit && !st.fallback) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
+        if (!k && st.jit_forms) return false;
         if (k) {
             void *a0 = lambda.data, *a1 = hl.data;
             void *args[4] = {&a0, &a1, &pacc, const_cast<PassParams<T2> *>(pp)};
@@ -1352,13 +1377,16 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
     int rc = 0;
     const char *jfe = std::getenv("PLB200_JIT_FORMS");
     const bool jit_forms = std::getenv("PLB200_EMU_JIT") != nullptr && !(jfe && jfe[0] == '0');
-    build_schedule<T2, Cfg>(n, 148, items, scaled, jit_forms, [&](const Step &st, const PassParams<T2> *pp) {
-        if (rc) return;
+    // PLB200_EMU_REFUSE=1: refuse every pass that needs a specialised kernel, as a consumer without that kernel does
+    const bool refuse = std::getenv("PLB200_EMU_REFUSE") != nullptr;
+    build_schedule<T2, Cfg>(n, 148, items, scaled, jit_forms, [&](const Step &st, const PassParams<T2> *pp) -> bool {
+        if (rc) return true;
         if (st.op >= 0) {
             stats[1]++;
             rc = standalone(ctx, st.op);
-            return;
+            return true;
         }
+        if (refuse && (st.jit_forms || st.jit_only)) return false;
         if (st.op == -2) {
             for (T2 *sv : {sv0, sv1}) {
                 if (!sv) continue;
@@ -1367,15 +1395,17 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
                     sv[i] = mk<T2>(v.real(), v.imag());
                 }
             }
-            return;
+            return true;
         }
         std::vector<double> acc(kMaxPassOps, 0.0);
-        if ((st.jit_only || st.jit_forms || std::getenv("PLB200_EMU_JIT")) && emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
+        if ((st.jit_only || st.jit_forms || (std::getenv("PLB200_EMU_JIT") && !st.fallback)) &&
+            emulate_pass_jit<T2, Cfg>(sv0, *pp, jit::Route{}, nullptr, sv1, acc.data())) {
         } else if (st.jit_only) fail("emu: a pass with two-bit pair ops has no specialised source");
         else if (st.ext) emulate_pass<T2, Cfg, true>(sv0, sv1, acc.data(), *pp);
         else emulate_pass<T2, Cfg, false>(sv0, sv1, acc.data(), *pp);
         for (size_t s = 0; s < st.slots.size(); s++) acc_host[st.slots[s]] += st.slot_scale[s] * acc[s];
         stats[0]++, stats[2] += st.nrounds, stats[3] += st.nops;
+        return true;
     });
     return rc;
 }

@@ -414,3 +414,27 @@ def test_jit_forms_special_angles_on_device(plb, ref, jit_sync, dtype):
     r = ref.StateVector(n, dtype)
     r.apply_ops(ops)
     np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=4 * TOL[np.dtype(dtype)])
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_refused_passes_fall_back_to_the_interpreter(plb, dtype, monkeypatch):
+    """Asynchronous tier, first sightings: a consumer without the pass's kernel refuses it (PLB200_EMU_REFUSE=1).
+    A pass in the jit forms comes back in the interpreter's encoding; a pass holding two- / four-bit pair ops is
+    cut at those ops — interpreter passes over the same tile in between, the pair ops stand-alone.  Same
+    amplitudes as the oracle either way, and nothing ran through generated code."""
+    from test_tile_emulation import emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "1")
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    monkeypatch.setenv("PLB200_EMU_REFUSE", "1")
+    n = 14
+    for ops in (_pair2_tape(n, 4, 150), circuits.random_circuit(n, 5, 3)):
+        st = random_state(n, dtype, 6)
+        before = emu.plb200_emu_jit_passes()
+        out, stats = emu_apply(emu, plb, n, ops, st, True)
+        assert emu.plb200_emu_jit_passes() == before  # every pass ran through the interpreter emulation
+        np.testing.assert_allclose(out, oracle_apply(n, ops, st), rtol=0, atol=2 * TOL[np.dtype(dtype)])
+        n_pair = sum(1 for o in ops if o["name"] in ("IsingXX", "IsingXY", "IsingYY", "SingleExcitation", "SingleExcitationPlus",
+                                                     "SingleExcitationMinus", "PSWAP", "DoubleExcitation"))
+        assert stats[1] >= n_pair and stats[0] >= 1, stats  # the pair ops ran stand-alone, the rest in tile passes
