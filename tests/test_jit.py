@@ -438,3 +438,37 @@ def test_refused_passes_fall_back_to_the_interpreter(plb, dtype, monkeypatch):
         n_pair = sum(1 for o in ops if o["name"] in ("IsingXX", "IsingXY", "IsingYY", "SingleExcitation", "SingleExcitationPlus",
                                                      "SingleExcitationMinus", "PSWAP", "DoubleExcitation"))
         assert stats[1] >= n_pair and stats[0] >= 1, stats  # the pair ops ran stand-alone, the rest in tile passes
+
+
+@pytest.mark.gpu
+def test_pair_ops_fused_in_the_default_tier(plb, ref, monkeypatch):
+    """Default (asynchronous) tier: a tape with IsingXX / SingleExcitation / DoubleExcitation ... is scheduled with
+    those gates INSIDE the tile passes.  First sightings have no kernel: the passes are cut at the pair ops
+    (interpreter pieces + stand-alone kernels).  After the background compile the whole tape runs as specialised
+    passes with no stand-alone kernel — and every run gives lightning.qubit's state."""
+    if not plb.jit_available():
+        pytest.fail("NVRTC / libcuda could not be loaded on a GPU box")
+    monkeypatch.setenv("PLB200_JIT_MIN_QUBITS", "12")
+    plb.jit_set_mode(1)
+    try:
+        n = 17
+        ops = _pair2_tape(n, 8, 160)
+        r = ref.StateVector(n)
+        r.apply_ops(ops)
+        expect = r.get_state()
+        blob = plb.OpsBlob(ops)
+        sched = (C.c_int64 * 4)()
+        assert plb.lib().plb200_schedule_stats(C.c_int64(n), 64, blob.ptr(), sched) == 0
+        assert sched[1] == 0 and sched[0] >= 2, list(sched)  # every gate of the tape sits in a tile pass
+        launches = []
+        for it in range(3):
+            sv = plb.StateVector(n)
+            sv.apply_ops(ops, fuse=True)
+            np.testing.assert_allclose(sv.get_state(), expect, rtol=0, atol=1e-12)
+            launches.append(sv.last_apply_stats()[1])
+            if it == 1:
+                plb.jit_wait()
+        # first sighting: interpreter pieces + stand-alone pair ops; with the kernels: one launch per pass
+        assert launches[0] > sched[0] and launches[2] == sched[0], (launches, list(sched))
+    finally:
+        plb.jit_set_mode(-1)
