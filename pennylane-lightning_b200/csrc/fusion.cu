@@ -456,9 +456,13 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         return;
     }
     auto cur = std::make_unique<PassParams<T2>>();
-    // PLB200_SCHED_GREEDY1=1 / PLB200_SCHED_MULTISTART=1 force the choice (tests fuzz both on small states)
+    // PLB200_SCHED_GREEDY1=1 / PLB200_SCHED_MULTISTART=1 force the choice (tests fuzz both on small states).
+    // The multi-start tile choice costs the host ~2 ms per pass (30q tape: 41 ms against 2.5 ms for plain greedy)
+    // and saves ~15 % of the passes: it pays once a pass takes the GPU longer than that, i.e. from 4 GiB states
+    // (c128: 28 qubits, 2.3 ms per pass); below, the host would be the bottleneck (26q: 21 ms of scheduling for
+    // 10 ms of GPU work).
     const bool multistart = std::getenv("PLB200_SCHED_MULTISTART") != nullptr ||
-                            ((sizeof(T2) << n) >= (size_t{1} << 30) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr);
+                            ((sizeof(T2) << n) >= (size_t{1} << 32) && std::getenv("PLB200_SCHED_GREEDY1") == nullptr);
     const uint64_t full = (n >= 64) ? ~uint64_t{0} : ((uint64_t{1} << n) - 1);
     std::vector<FOp> f(items.size());
     const bool pair2 = Cfg::NS == 1 && pair2_enabled(n);
