@@ -472,7 +472,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
     }
     std::vector<char> done(items.size(), 0);
     size_t first = 0;
-    const size_t window = 512;
+    const size_t window = std::getenv("PLB200_SCHED_WINDOW") ? static_cast<size_t>(std::atoi(std::getenv("PLB200_SCHED_WINDOW"))) : 512;
     const uint64_t lowbits = (uint64_t{1} << LOW) - 1;
     const size_t max_pass_ops = kMaxPassOps - kMaxPassRounds - 2 - 24; // emitted ops; room for scalar ops + ladder headers
     std::vector<int> pending, exec;
