@@ -234,6 +234,9 @@ bool is_pair4(const COp &op) {
     return true;
 }
 
+// dense 4x4 on two wires (QubitUnitary, K_DENSE2)
+bool is_dense2(const COp &op) { return op.kind == OP_DENSE && op.tbits.size() == 2 && op.mat.size() == 16; }
+
 FOp classify(const COp &op, bool pair2 = false, int reg_bits = 4) {
     FOp f;
     uint64_t t = 0;
@@ -247,7 +250,7 @@ FOp classify(const COp &op, bool pair2 = false, int reg_bits = 4) {
     } else if (is_swap2(op)) {
         f.fusable = true;
         f.nd = t;
-    } else if (pair2 && (is_pair2(op) || (reg_bits >= 4 && is_pair4(op)))) {
+    } else if (pair2 && (is_pair2(op) || (reg_bits >= 4 && is_pair4(op)) || is_dense2(op))) {
         f.fusable = true;
         f.nd = t;
     } else if (op.kind == OP_DIAG) {
@@ -524,7 +527,9 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             size_t emitted = 0, keep = 0;
             for (int i : exec) {
                 const AdjItem &it = items[i];
-                if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op))
+                if (!it.overlap && it.op.kind == OP_DENSE)
+                    emitted += 4; // K_DENSE2: one record per matrix row
+                else if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op))
                     emitted += 2 * it.op.blocks.size(); // K_PAIR2 / K_PAIR4: one record per block (+ a pivot each at most)
                 else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG && it.op.cmask != 0 &&
                          __builtin_popcountll(f[i].pmask) == 1 && f[i].d[0] != cd(1.0))
@@ -679,7 +684,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 uint64_t pmask = it.overlap ? (it.pw.x ? 0 : it.pw.z) : (it.op.kind == OP_PAIRS ? 0 : fo.pmask);
                 cd d0 = fo.d[0], d1 = fo.d[1];
                 if (phase_S) cmask = cval = phase_S, pmask = 0, d0 = d1 = phase;
-                const bool is_diag = !it.overlap && it.op.kind != OP_PAIRS;
+                const bool is_diag = !it.overlap && it.op.kind == OP_DIAG;
                 if (is_diag) {
                     if (pmask == 0) { // one scalar d0 == d1 on the control subspace
                         if (cmask == 0 && allow_scaled) {
@@ -730,6 +735,19 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 } else if (is_swap2(it.op)) {
                     st.ext = true;
                     t.code = make_code(cm_reg ? K_SWAP2_M : K_SWAP2, reg_pos(it.op.tbits[0]), reg_pos(it.op.tbits[1]));
+                } else if (it.op.kind == OP_DENSE) {
+                    // dense 4x4 on two register bits: header record (row 0) + three continuation records (rows 1-3)
+                    st.jit_only = true;
+                    t.code = make_code(K_DENSE2, reg_pos(it.op.tbits[0]), reg_pos(it.op.tbits[1]));
+                    if (t.cm_tid | t.cmask_o) t.code |= F_COND;
+                    for (int row = 0; row < 4; row++) {
+                        TileOp<T2> rec;
+                        if (row == 0) rec = t;
+                        else std::memset(&rec, 0, sizeof(rec));
+                        for (int q = 0; q < 4; q++) rec.m[q] = mk<T2>(it.op.mat[row * 4 + q].real(), it.op.mat[row * 4 + q].imag());
+                        top[op_cursor++] = rec;
+                    }
+                    return;
                 } else if (it.op.kind == OP_PAIRS && (it.op.tbits.size() == 2 || it.op.tbits.size() == 4)) {
                     // two- / four-bit pair op: one K_PAIR2 / K_PAIR4 record per 2x2 block (a pivot X on the pair first
                     // when needed)
@@ -916,7 +934,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 // non-diagonal action on register bits: parked phases on those bits must come first
                 uint64_t ndbits = 0;
                 if (it.overlap) ndbits = it.pw.x;
-                else if (it.op.kind == OP_PAIRS)
+                else if (it.op.kind == OP_PAIRS || it.op.kind == OP_DENSE)
                     for (int b : it.op.tbits) ndbits |= uint64_t{1} << b;
                 for (int i = 0; i < R; i++)
                     if (ndbits >> hq.tbits[rl[i]] & 1) flush_bucket(i);
@@ -981,7 +999,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 };
                 auto needs_kernel = [&](int idx) {
                     const AdjItem &it = items[idx];
-                    return !it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op);
+                    return !it.overlap && ((it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op)) || it.op.kind == OP_DENSE);
                 };
                 for (size_t r = 0; r < hp.rounds.size(); r++) {
                     std::vector<int> run;

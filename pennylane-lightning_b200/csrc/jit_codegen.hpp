@@ -357,6 +357,15 @@ template <typename T2, class Cfg> class Gen {
         return true;
     }
 
+    // records that follow op K and belong to it (ladder entries, rows 1-3 of a dense 4x4)
+    int extra_records(int K) const {
+        const TileOp<T2> &o = pp.ops[K];
+        const int kind = code_kind(o.code);
+        if (kind == K_LADDER) return ladder_records<T2>(static_cast<int>(o.slot)) - 1;
+        if (kind == K_DENSE2) return 3;
+        return 0;
+    }
+
     // from_global / to_global: the round's registers come from / go to the state vector instead of the tile
     // round r of the pass; r == nrounds: the op-less TRANSFER round a routed pass appends when its last round is
     // not line-coalesced (register bits = the highest tile bits; it replaces the store phase at the same cost)
@@ -436,11 +445,9 @@ template <typename T2, class Cfg> class Gen {
         for (int k = 0; k < rh.nops + rh.nlad; k++) {
             const TileOp<T2> &o = pp.ops[rh.first_op + k];
             const int kind = code_kind(o.code);
-            if (kind == K_LADDER) {
-                if (code_p(o.code) >= R) r_ladder = true;
-                k += ladder_records<T2>(static_cast<int>(o.slot)) - 1;
-            } else if (kind == K_DIAG_T || kind == K_DIAG1_T)
-                n_tscalar++;
+            if (kind == K_LADDER && code_p(o.code) >= R) r_ladder = true;
+            if (kind == K_DIAG_T || kind == K_DIAG1_T) n_tscalar++;
+            k += extra_records(rh.first_op + k);
         }
         const bool merge_ts = n_tscalar >= 2 || r_ladder;
         if (merge_ts) s += "    T2 ts; ts.x = (real)1; ts.y = (real)0; bool ts_any = false;\n";
@@ -461,6 +468,7 @@ template <typename T2, class Cfg> class Gen {
                 cur_set = 'v';
             }
             gen_op(K, merge_ts, true);
+            k += extra_records(K);
         }
 
         if (merge_ts) {
@@ -624,6 +632,22 @@ template <typename T2, class Cfg> class Gen {
             pairs_on(P, pr);
             const char *fn = kind == K_SROT_R ? "srot_r_t" : kind == K_SROT_I ? "srot_i_t" : kind == K_SROK_R ? "srot_r_k" : "srot_i_k";
             for (auto [u0, u1] : pr) add("            %s(%s, %s, m0.x);\n", fn, V(u0).c_str(), V(u1).c_str());
+            close_cond();
+        } break;
+        case K_DENSE2: { // out[j] = sum_c M[j][c] in[c] on the register quadruples over bits P (matrix bit 0), C (bit 1)
+            open_cond();
+            for (int u = 0; u < NV; u++) {
+                if (((u >> P) & 1) || ((u >> C) & 1) || !((op.umask >> u) & 1u)) continue;
+                const int q[4] = {u, u | (1 << P), u | (1 << C), u | (1 << P) | (1 << C)};
+                s += "            {\n";
+                for (int c = 0; c < 4; c++) add("                const T2 o%d = %s;\n", c, V(q[c]).c_str());
+                for (int j = 0; j < 4; j++) {
+                    add("                T2 n%d = o0; cmul_ip(n%d, pp.ops[%d].m[0]);\n", j, j, K + j);
+                    for (int c = 1; c < 4; c++) add("                cshear_ip(n%d, pp.ops[%d].m[%d], o%d);\n", j, K + j, c, c);
+                }
+                for (int j = 0; j < 4; j++) add("                %s = n%d;\n", V(q[j]).c_str(), j);
+                s += "            }\n";
+            }
             close_cond();
         } break;
         case K_SWAP: case K_SWAP_M: case K_SWAP_CR: case K_SWAP2: case K_SWAP2_M: {

@@ -147,12 +147,17 @@ enum : int {
     // pos3 << 21 (a, b: 4-bit values over the target bits, pos_j: register bit carrying target bit j).  Specialised
     // kernels only, like K_PAIR2.
     K_PAIR4 = 31,
+    // Dense 4x4 matrix on TWO register bits P (matrix bit 0) and C (matrix bit 1) — QubitUnitary on two wires and its
+    // controlled forms.  Four records: record j carries row j of the matrix in m[0..3]; only the first is an op.
+    // Specialised kernels only.
+    K_DENSE2 = 32,
     K_LAST_OVL = K_OVL_D,
     K_FIRST_DIAG = K_DIAG_R,
     K_FIRST_OVL = K_OVL_X,
 };
 // Code word of an op: bits 0-7 = dense case index of apply_gate's switch (one jump table), bits 8-12 =
-// kind, bits 13-15 = P, bits 16-18 = C, then flags.
+// kind (bit 19: its sixth bit, kinds >= 32 exist in the specialised kernels only), bits 13-15 = P, bits 16-18 = C,
+// then flags.
 constexpr uint32_t F_COND = 1u << 20; // has controls (outside / thread bits): needs the predicate
 constexpr uint32_t F_PAR = 1u << 21;  // phase depends on a thread / outside parity
 constexpr uint32_t F_OVL = 1u << 22;  // adjoint overlap op
@@ -172,10 +177,11 @@ PLB_HD constexpr int pc_index(int p, int c) { return p * (kMaxR - 1) + (c < p ? 
 PLB_HD constexpr uint32_t make_code(int kind, int p, int c) {
     const int n = kind_cases(kind);
     const int sub = n == kMaxR * (kMaxR - 1) ? pc_index(p, c) : n == kMaxR ? p : 0;
-    return static_cast<uint32_t>(kind_base(kind) + sub) | static_cast<uint32_t>(kind) << 8 |
-           static_cast<uint32_t>(p) << 13 | static_cast<uint32_t>(c) << 16 | ((kind >= K_FIRST_OVL && kind <= K_LAST_OVL) ? F_OVL : 0u);
+    return static_cast<uint32_t>((kind_base(kind) + sub) & 255) | static_cast<uint32_t>(kind & 31) << 8 |
+           static_cast<uint32_t>(kind >> 5) << 19 | static_cast<uint32_t>(p) << 13 | static_cast<uint32_t>(c) << 16 |
+           ((kind >= K_FIRST_OVL && kind <= K_LAST_OVL) ? F_OVL : 0u);
 }
-PLB_HD constexpr int code_kind(uint32_t code) { return static_cast<int>((code >> 8) & 31u); }
+PLB_HD constexpr int code_kind(uint32_t code) { return static_cast<int>(((code >> 8) & 31u) | (((code >> 19) & 1u) << 5)); }
 PLB_HD constexpr int code_p(uint32_t code) { return static_cast<int>((code >> 13) & 7u); }
 
 template <typename T2> struct alignas(16) TileOp {

@@ -472,3 +472,69 @@ def test_pair_ops_fused_in_the_default_tier(plb, ref, monkeypatch):
         assert launches[0] > sched[0] and launches[2] == sched[0], (launches, list(sched))
     finally:
         plb.jit_set_mode(-1)
+
+
+def _unitary_tape(n, seed, count=90):
+    """Rotations / CNOTs mixed with Haar-ish random unitaries on two wires (QubitUnitary), some controlled."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(count):
+        r = rng.random()
+        if r < 0.4:
+            ops.append(circuits.op(("RX", "RY", "RZ")[int(rng.integers(3))], [int(rng.integers(n))], [rng.uniform(0, 6)]))
+        elif r < 0.55:
+            ops.append(circuits.op("CNOT", [int(x) for x in rng.permutation(n)[:2]]))
+        else:
+            a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+            q, rr = np.linalg.qr(a)
+            u = q * (np.diag(rr) / np.abs(np.diag(rr)))
+            w = [int(x) for x in rng.permutation(n)[:4]]
+            ctrl = w[2:3] if rng.random() < 0.3 else []
+            o = circuits.op("QubitUnitary", w[:2], [], inverse=bool(rng.integers(2)), ctrl_wires=ctrl,
+                            ctrl_values=[bool(rng.integers(2))] * len(ctrl))
+            o["matrix"] = u
+            ops.append(o)
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_two_wire_unitaries_fused_on_host(plb, dtype, monkeypatch):
+    """QubitUnitary on two wires (also controlled, also inverted) as K_DENSE2 tile ops of the generated code: no
+    stand-alone kernel, the oracle's amplitudes; refused (no kernel yet) they run stand-alone between interpreter
+    pieces with the same result."""
+    from test_tile_emulation import emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "1")
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 14
+    ops = _unitary_tape(n, 12)
+    n_u = sum(1 for o in ops if o["name"] == "QubitUnitary")
+    st = random_state(n, dtype, 4)
+    expect = oracle_apply(n, ops, st)
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    assert stats[1] == 0 and stats[3] == len(ops), stats
+    np.testing.assert_allclose(out, expect, rtol=0, atol=2 * TOL[np.dtype(dtype)])
+    monkeypatch.setenv("PLB200_EMU_REFUSE", "1")
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    assert stats[1] >= n_u, stats
+    np.testing.assert_allclose(out, expect, rtol=0, atol=2 * TOL[np.dtype(dtype)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_two_wire_unitaries_fused_on_device(plb, ref, jit_sync, dtype):
+    """QubitUnitary on two wires inside the specialised passes (K_DENSE2) against lightning.qubit; one launch per
+    pass, nothing stand-alone."""
+    n = 17
+    ops = _unitary_tape(n, 21, 140)
+    blob = plb.OpsBlob(ops)
+    sched = (C.c_int64 * 4)()
+    assert plb.lib().plb200_schedule_stats(C.c_int64(n), 64 if dtype == np.complex128 else 32, blob.ptr(), sched) == 0
+    assert sched[1] == 0, list(sched)
+    a = plb.StateVector(n, dtype)
+    a.apply_ops(blob, fuse=True)
+    assert a.last_apply_stats()[1] == sched[0]
+    r = ref.StateVector(n, dtype)
+    r.apply_ops(ops)
+    np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=2 * TOL[np.dtype(dtype)])
