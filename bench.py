@@ -279,6 +279,45 @@ def extra_qft(plb, circuits, n, dtype, tag, stream, peak):
             "tolerance": tol, "pass": bool(err <= tol)}
 
 
+def extra_c64(plb, circuits, stream, peak, n=30, steps=5):
+    """The headline tape in single precision (c64): device-resident fused rate and per-pass HBM fraction, with
+    <Z_w> on every wire compared against the c128 run of the same tape (tolerance 1e-5, north_star's for c64)."""
+    import torch
+
+    ops = circuits.random_circuit(n, DEPTH, SEED)
+    blob = plb.OpsBlob(ops)
+    zw = [[w] for w in range(n)]
+    ref = plb.StateVector(n, np.complex128, torch.cuda.current_device(), stream)
+    ref.apply_ops(blob, fuse=True)
+    z128 = np.asarray(ref.expval_pauli_words_each(["Z"] * n, zw))
+    del ref
+    torch.cuda.empty_cache()
+    sv = plb.StateVector(n, np.complex64, torch.cuda.current_device(), stream)
+    for it in range(3):  # sightings 1-2 let the kernels be compiled, 3 loads them
+        if it == 2 and plb.jit_enabled():
+            torch.cuda.synchronize()
+            plb.jit_wait()
+        sv.reset()
+        sv.apply_ops(blob, fuse=True)
+    z64 = np.asarray(sv.expval_pauli_words_each(["Z"] * n, zw))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sv.apply_ops(blob, fuse=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    passes = sv.last_apply_stats()[1]
+    S = (1 << n) * 8
+    err = float(np.max(np.abs(z64 - z128)))
+    del sv
+    return {"qubits": n, "dtype": "c64", "gates": len(ops), "ms_per_step": ms, "gates_per_s": len(ops) / (ms * 1e-3),
+            "hbm_passes": passes, "roofline_frac": passes * 2 * S / (ms * 1e-3) / 1e9 / peak,
+            "roofline_def": "passes x 2S / time / peak", "max_abs_err_expval_z_vs_c128": err, "tolerance": 1e-5,
+            "pass": bool(err <= 1e-5)}
+
+
 def extra_sampling(plb, circuits, stream, peak, n=30, shots=100000):
     """Computational-basis samples of the config-2 state with the table-free device sampler (one sweep for the chunk
     masses, a scan, one warp per shot); checked through every single-wire marginal against <Z_w>."""
@@ -733,6 +772,7 @@ def run_ours(args):
             for key, fn in (("config3_qft33_c128", lambda: extra_qft(plb, circuits, 33, np.complex128, "c128", stream, peak)),
                             ("config3_qft33_c64", lambda: extra_qft(plb, circuits, 33, np.complex64, "c64", stream, peak)),
                             ("config5_adjoint_24q_1000", lambda: extra_adjoint(plb, lq_ref, circuits, stream, peak)),
+                            ("config2_30q_c64", lambda: extra_c64(plb, circuits, stream, peak, nloc)),
                             ("sampling_30q_device", lambda: extra_sampling(plb, circuits, stream, peak, nloc))):
                 try:
                     extra[key] = fn()

@@ -913,6 +913,8 @@ template <typename T2, class Cfg> class Gen {
         // packed FP32 (FFMA2) is opt-in: measured SLOWER on the 30-qubit c64 tape (182 vs 124 ms): the 64-bit
         // register-pair alignment of FFMA2 operands costs MOVs and spills that outweigh the halved FMA count
         add("#define PLB_NO_FFMA2 %d\n", std::getenv("PLB200_JIT_FFMA2") ? 0 : 1);
+        // L2 prefetch distance in tiles of this CTA (tuning knob; 1 = the next tile, 0 = none)
+        add("#define PLB_PREFETCH %dull\n", std::getenv("PLB200_JIT_PREFETCH") ? std::max(0, std::atoi(std::getenv("PLB200_JIT_PREFETCH"))) : 1);
         add("#define PLB_MAXROUNDS %d\n#define PLB_MAXOPS %d\n#define PLB_SWZ_B %d\n#define PLB_SWZ_COLS 0x%llxull\n", kMaxPassRounds,
             kMaxPassOps, Swz<T2>::B, static_cast<unsigned long long>(Swz<T2>::cols));
         add("#define PLB_SIZEOF_TILEOP %zu\n#define PLB_SIZEOF_PASSPARAMS %zu\n#define PLB_OFFSETOF_OPS %zu\n", sizeof(TileOp<T2>),
@@ -973,8 +975,8 @@ template <typename T2, class Cfg> class Gen {
              "    const u32 tid = threadIdx.x;\n"
              "    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {\n"
              "        const u64 base = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t, rp)" : "t") + ", pp.hdr.tile_ins);\n"
-             "        if (t + gridDim.x < pp.hdr.ntiles) {\n"
-             "            const u64 nbase = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t + gridDim.x, rp)" : "t + gridDim.x") + ", pp.hdr.tile_ins);\n"
+             "        if (PLB_PREFETCH > 0 && t + PLB_PREFETCH * gridDim.x < pp.hdr.ntiles) {\n"
+             "            const u64 nbase = insert_bits_m(" + std::string(route.k > 0 ? "route_tile(t + PLB_PREFETCH * gridDim.x, rp)" : "t + PLB_PREFETCH * gridDim.x") + ", pp.hdr.tile_ins);\n"
              "            for (int l = tid; l < (1 << (PLB_M - PLB_LOW)); l += PLB_NT)\n"
              "                asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(sv + (nbase | goff[l])));\n"
              "        }\n" +
