@@ -13,7 +13,7 @@
 // Adjoint variant (AdjointJacobianLQubit.hpp:269-314 as ONE sweep per block of ops): the tile of
 // lambda and the tile of H·lambda travel together; walking the tape backwards, a trainable op first
 // contributes its overlap Im<H lambda| G |lambda> (G = (controlled) X / Y / Z-parity generator)
-// from registers — accumulated per CTA in shared memory, flushed once with fp64 atomics — and then
+// from registers — accumulated per warp in shared memory, per CTA in a partials buffer, reduced in a fixed order — and then
 // its inverse is applied to both tiles.  No mu copy, no per-op HBM sweep.
 //
 // Gate commutation used by the scheduler: ops acting on disjoint bit sets commute, nothing else.
@@ -45,18 +45,37 @@ namespace {
 using namespace tile;
 
 #if !defined(PLB200_HOST_EMU)
+// Overlap accumulation of the two-state (adjoint) passes, in a FIXED order: the lanes of a warp are summed by a
+// shuffle tree, every warp owns a row of the CTA's shared accumulators (no atomics; a warp walks its tiles in
+// order), the rows are added in warp order at the end of the kernel into this CTA's row of a global partials
+// buffer, and overlap_reduce_kernel adds the CTAs' rows in CTA order.  Same grid -> same bits, run after run.
 struct WarpReduce {
-    double *acc;
+    double *acc; // this warp's row
     __host__ __device__ __forceinline__ void operator()(int slot, double s) const {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&acc[slot], s);
+        if ((threadIdx.x & 31) == 0) acc[slot] += s;
 #else
         (void)slot, (void)s;
 #endif
     }
 };
+// out[i] = sum over CTAs b (ascending) of part[b * nslots + i]; one thread per slot, four independent chains
+__global__ void overlap_reduce_kernel(const double *__restrict__ part, unsigned nctas, int nslots, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    unsigned b = 0;
+    for (; b + 4 <= nctas; b += 4) {
+        s0 += part[static_cast<size_t>(b) * nslots + i];
+        s1 += part[static_cast<size_t>(b + 1) * nslots + i];
+        s2 += part[static_cast<size_t>(b + 2) * nslots + i];
+        s3 += part[static_cast<size_t>(b + 3) * nslots + i];
+    }
+    for (; b < nctas; b++) s0 += part[static_cast<size_t>(b) * nslots + i];
+    out[i] = (s0 + s1) + (s2 + s3);
+}
 
 template <typename T2, class Cfg, bool EXT>
 __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
@@ -74,11 +93,11 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
     // global offset of every 2^LOW-amplitude line of a tile, from the tile's bit positions
     for (int i = threadIdx.x; i < (1 << (M - LOW)); i += NT) goff[i] = tile_line_offset<M, LOW>(pp.hdr, i);
     if constexpr (NS == 2)
-        for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT) acc[i] = 0.0;
+        for (int i = threadIdx.x; i < pp.hdr.nslots * (NT / 32); i += NT) acc[i] = 0.0;
     __syncthreads();
     const uint32_t tid = threadIdx.x;
     const int nrounds = pp.hdr.nrounds;
-    const WarpReduce red{acc};
+    const WarpReduce red{acc + (threadIdx.x >> 5) * pp.hdr.nslots};
 
     for (uint64_t t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {
         const uint64_t base = insert_bits(t, pp.hdr.tile_ins);
@@ -102,9 +121,12 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
         if constexpr (NS == 2) E::store_tile(tid, base, goff, sv1, tile1);
         __syncthreads();
     }
-    if constexpr (NS == 2) {
-        for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT)
-            if (acc[i] != 0.0) atomicAdd(&acc_g[i], acc[i]);
+    if constexpr (NS == 2) { // acc_g: the partials buffer, one row of nslots per CTA
+        for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT) {
+            double t = 0.0;
+            for (int w = 0; w < NT / 32; w++) t += acc[w * pp.hdr.nslots + i];
+            acc_g[static_cast<size_t>(blockIdx.x) * pp.hdr.nslots + i] = t;
+        }
     }
 }
 #endif // !PLB200_HOST_EMU
@@ -1030,7 +1052,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
 
 template <class Cfg, typename T2> size_t smem_bytes_for() {
     return Cfg::NS * (sizeof(T2) << Cfg::M) + (sizeof(uint64_t) << (Cfg::M - Cfg::LOW)) +
-           (Cfg::NS == 2 ? sizeof(double) * kMaxPassOps : 0);
+           (Cfg::NS == 2 ? sizeof(double) * kMaxPassOps * ((1u << (Cfg::M - Cfg::R)) / 32) : 0); // one accumulator row per warp
 }
 
 std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
@@ -1231,7 +1253,11 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
     // device accumulators: one slab of kMaxPassOps doubles per tile pass; a pass executes >= 2 items
     const size_t max_pass = items.size() / 2 + 1;
     const size_t acc_bytes = max_pass * kMaxPassOps * sizeof(double);
-    double *dacc = static_cast<double *>(lambda.plan_buf(acc_bytes));
+    // + the per-CTA partials of the pass in flight (reduced in CTA order right after it: deterministic)
+    const size_t max_grid = static_cast<size_t>(lambda.sm_count) * 3 * 64;
+    const size_t part_bytes = max_grid * kMaxPassOps * sizeof(double);
+    double *dacc = static_cast<double *>(lambda.plan_buf(acc_bytes + part_bytes));
+    double *dpart = dacc + max_pass * kMaxPassOps;
     PLB_CUDA(cudaMemsetAsync(dacc, 0, acc_bytes, lambda.stream));
     struct PassSlots {
         std::vector<int> slots;
@@ -1258,12 +1284,17 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         jit::Kernel k;
         if (use_jit && !st.fallback) k = jit::lookup(jit::generate_pass_source<T2, Cfg>(*pp), lambda.device, smem_bytes_for<Cfg, T2>());
         if (!k && st.jit_forms) return false;
+        PLB_CHECK(st.grid <= max_grid, "fusion: adjoint pass grid exceeds the partials buffer");
         if (k) {
             void *a0 = lambda.data, *a1 = hl.data;
-            void *args[4] = {&a0, &a1, &pacc, const_cast<PassParams<T2> *>(pp)};
+            void *args[4] = {&a0, &a1, &dpart, const_cast<PassParams<T2> *>(pp)};
             jit::launch_args(k, st.grid, 1u << (Cfg::M - Cfg::R), smem_bytes_for<Cfg, T2>(), lambda.stream, args);
         } else
-            launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data), pacc, *pp);
+            launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data), dpart, *pp);
+        if (pp->hdr.nslots > 0) {
+            overlap_reduce_kernel<<<(pp->hdr.nslots + 127) / 128, 128, 0, lambda.stream>>>(dpart, st.grid, pp->hdr.nslots, pacc);
+            PLB_CUDA(cudaGetLastError());
+        }
         lambda.launches++;
         passes.push_back({st.slots, st.slot_scale});
         stats[0]++;

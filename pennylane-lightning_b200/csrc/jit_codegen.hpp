@@ -219,10 +219,10 @@ DEV double re_cb(const T2 a, const T2 b) { return (double)a.x * (double)b.x + (d
 #if defined(PLB_JIT_HOST)
 DEV void ovl_reduce(double *acc, int slot, double s) { acc[slot] += s; }
 #else
-DEV void ovl_reduce(double *acc, int slot, double s) {
+DEV void ovl_reduce(double *acc, int slot, double s) { // acc: this WARP's row of the CTA's accumulators: fixed order, no atomics
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&acc[slot], s);
+    if ((threadIdx.x & 31) == 0) acc[slot] += s;
 }
 #endif
 DEV u64 insert_bits_m(u64 x, const BitInsert &bi) {
@@ -846,14 +846,14 @@ template <typename T2, class Cfg> class Gen {
         return v > 0 ? v : std::max(1, 512 / (1 << NTB));
     }
 
-    // drivers of an adjoint pass: two tiles travel together, overlaps accumulate per CTA in shared memory and are
-    // flushed once per CTA with fp64 atomics (as tile_kernel does)
+    // drivers of an adjoint pass: two tiles travel together, overlaps accumulate per warp in shared memory and leave
+    // as one row of per-CTA partials (as tile_kernel does; the host reduces the rows in CTA order)
     void gen_two_state_drivers(int nr) {
         std::string dev, host;
         for (int r = 0; r < nr; r++) {
-            const std::string call = "round_" + std::to_string(r) + "(pp, tid, base, smem, smem1, acc)";
-            dev += "        " + call + "; __syncthreads();\n";
-            host += "        for (u32 tid = 0; tid < PLB_NT; tid++) { " + call + "; }\n";
+            const std::string call = "round_" + std::to_string(r) + "(pp, tid, base, smem, smem1, ";
+            dev += "        " + call + "accw); __syncthreads();\n";
+            host += "        for (u32 tid = 0; tid < PLB_NT; tid++) { " + call + "acc); }\n";
         }
         s += "#if defined(PLB_JIT_HOST)\n"
              "extern \"C\" void plb_pass_host(T2 *sv, const PassParams *ppp, const RouteParams *, T2 *sv1, double *acc) {\n"
@@ -875,9 +875,10 @@ template <typename T2, class Cfg> class Gen {
              "    u64 *goff = (u64 *)(smem + 2 * (sizeof(T2) << PLB_M));\n"
              "    double *acc = (double *)(goff + (1 << (PLB_M - PLB_LOW)));\n"
              "    for (int i = threadIdx.x; i < (1 << (PLB_M - PLB_LOW)); i += PLB_NT) goff[i] = tile_line_offset(pp.hdr, i);\n"
-             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT) acc[i] = 0.0;\n"
+             "    for (int i = threadIdx.x; i < pp.hdr.nslots * (PLB_NT / 32); i += PLB_NT) acc[i] = 0.0;\n"
              "    __syncthreads();\n"
              "    const u32 tid = threadIdx.x;\n"
+             "    double *accw = acc + (threadIdx.x >> 5) * pp.hdr.nslots; // one accumulator row per warp\n"
              "    for (u64 t = blockIdx.x; t < pp.hdr.ntiles; t += gridDim.x) {\n"
              "        const u64 base = insert_bits_m(t, pp.hdr.tile_ins);\n"
              "        if (t + gridDim.x < pp.hdr.ntiles) {\n"
@@ -895,8 +896,11 @@ template <typename T2, class Cfg> class Gen {
              "        store_tile(tid, base, goff, sv1, smem1);\n"
              "        __syncthreads();\n"
              "    }\n"
-             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT)\n"
-             "        if (acc[i] != 0.0) atomicAdd(&acc_g[i], acc[i]);\n"
+             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT) { // rows in warp order -> this CTA's row of the partials\n"
+             "        double t = 0.0;\n"
+             "        for (int w = 0; w < PLB_NT / 32; w++) t += acc[w * pp.hdr.nslots + i];\n"
+             "        acc_g[(size_t)blockIdx.x * pp.hdr.nslots + i] = t;\n"
+             "    }\n"
              "}\n"
              "#endif\n";
     }

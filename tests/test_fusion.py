@@ -122,6 +122,10 @@ def test_fused_adjoint_matches_reference(plb, ref, dtype):
     jb = b.adjoint_jacobian([ham_b], ops, tp, apply_ops=True)
     tol = 1e-11 if dtype == np.complex128 else 2e-4
     np.testing.assert_allclose(ja, jb, rtol=0, atol=tol)
+    # the overlaps are accumulated in a fixed order (per warp, per CTA, CTAs in index order): bit-identical reruns
+    for _ in range(3):
+        c = plb.StateVector(n, dtype)
+        np.testing.assert_array_equal(c.adjoint_jacobian([ham_a], ops, tp, apply_ops=True), ja)
     # the un-fused sweep (env switch) gives the same numbers
     import os
     os.environ["PLB200_ADJOINT_UNFUSED"] = "1"

@@ -244,6 +244,7 @@ def test_jit_adjoint_passes_match_reference(plb, ref, jit_sync, dtype):
     assert after["jit_launches"] > before["jit_launches"] and after["failed"] == before["failed"]
     jr = r.adjoint_jacobian([ham_r], ops, tp, apply_ops=True)
     np.testing.assert_allclose(ja, jr, rtol=0, atol=1e-11 if dtype == np.complex128 else 2e-4)
+    np.testing.assert_array_equal(a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True), ja)  # fixed-order sums
     plb.jit_set_mode(0)
     ji = a.adjoint_jacobian([ham_a], ops, tp, apply_ops=True)
     plb.jit_set_mode(2)
