@@ -61,20 +61,22 @@ struct WarpReduce {
 #endif
     }
 };
-// out[i] = sum over CTAs b (ascending) of part[b * nslots + i]; one thread per slot, four independent chains
-__global__ void overlap_reduce_kernel(const double *__restrict__ part, unsigned nctas, int nslots, double *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nslots) return;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    unsigned b = 0;
-    for (; b + 4 <= nctas; b += 4) {
-        s0 += part[static_cast<size_t>(b) * nslots + i];
-        s1 += part[static_cast<size_t>(b + 1) * nslots + i];
-        s2 += part[static_cast<size_t>(b + 2) * nslots + i];
-        s3 += part[static_cast<size_t>(b + 3) * nslots + i];
+// out[i] = sum over CTAs of part[i * nctas + b] (slot-major partials): one block per slot, thread t adds the CTAs
+// t, t + 256, ... in that order, then the 256 partial sums are added by a fixed shuffle / shared-memory tree
+__global__ void __launch_bounds__(256) overlap_reduce_kernel(const double *__restrict__ part, unsigned nctas, double *__restrict__ out) {
+    __shared__ double sm[8];
+    const double *col = part + static_cast<size_t>(blockIdx.x) * nctas;
+    double s = 0;
+    for (unsigned b = threadIdx.x; b < nctas; b += 256) s += col[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += sm[w];
+        out[blockIdx.x] = t;
     }
-    for (; b < nctas; b++) s0 += part[static_cast<size_t>(b) * nslots + i];
-    out[i] = (s0 + s1) + (s2 + s3);
 }
 
 template <typename T2, class Cfg, bool EXT>
@@ -121,11 +123,11 @@ __global__ void __launch_bounds__(1 << (Cfg::M - Cfg::R), Cfg::MINB)
         if constexpr (NS == 2) E::store_tile(tid, base, goff, sv1, tile1);
         __syncthreads();
     }
-    if constexpr (NS == 2) { // acc_g: the partials buffer, one row of nslots per CTA
+    if constexpr (NS == 2) { // acc_g: the partials buffer, slot-major (one row of gridDim.x CTAs per slot)
         for (int i = threadIdx.x; i < pp.hdr.nslots; i += NT) {
             double t = 0.0;
             for (int w = 0; w < NT / 32; w++) t += acc[w * pp.hdr.nslots + i];
-            acc_g[static_cast<size_t>(blockIdx.x) * pp.hdr.nslots + i] = t;
+            acc_g[static_cast<size_t>(i) * gridDim.x + blockIdx.x] = t;
         }
     }
 }
@@ -1292,7 +1294,7 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         } else
             launch_pass<T2, Cfg>(st, lambda.stream, static_cast<T2 *>(lambda.data), static_cast<T2 *>(hl.data), dpart, *pp);
         if (pp->hdr.nslots > 0) {
-            overlap_reduce_kernel<<<(pp->hdr.nslots + 127) / 128, 128, 0, lambda.stream>>>(dpart, st.grid, pp->hdr.nslots, pacc);
+            overlap_reduce_kernel<<<pp->hdr.nslots, 256, 0, lambda.stream>>>(dpart, st.grid, pacc);
             PLB_CUDA(cudaGetLastError());
         }
         lambda.launches++;

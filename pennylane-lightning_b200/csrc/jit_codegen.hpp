@@ -896,10 +896,10 @@ template <typename T2, class Cfg> class Gen {
              "        store_tile(tid, base, goff, sv1, smem1);\n"
              "        __syncthreads();\n"
              "    }\n"
-             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT) { // rows in warp order -> this CTA's row of the partials\n"
+             "    for (int i = threadIdx.x; i < pp.hdr.nslots; i += PLB_NT) { // rows in warp order -> this CTA's column of the slot-major partials\n"
              "        double t = 0.0;\n"
              "        for (int w = 0; w < PLB_NT / 32; w++) t += acc[w * pp.hdr.nslots + i];\n"
-             "        acc_g[(size_t)blockIdx.x * pp.hdr.nslots + i] = t;\n"
+             "        acc_g[(size_t)i * gridDim.x + blockIdx.x] = t;\n"
              "    }\n"
              "}\n"
              "#endif\n";
