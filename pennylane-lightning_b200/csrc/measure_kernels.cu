@@ -3,15 +3,14 @@
 // launch), small-matrix expval, Pauli-sum (Hamiltonian) application, state preparation helpers
 // and the local half of the distributed index-bit swap.
 // All sums accumulate in fp64 per thread, reduce by warp shuffle, then by a fixed-order second
-// stage -> deterministic for a given launch shape.  Two exceptions accumulate with fp64 atomics and are NOT bitwise
-// reproducible run to run (the order of the additions varies): probs_hist_kernel (marginals over <= 11 wires:
-// shared-memory histogram per CTA, then global atomics) and the overlap accumulators of the fused adjoint passes
-// (fusion.cu).  Their results agree with the reference to the stated tolerance, not to the last bit.
+// stage -> deterministic for a given launch shape: no reduction of the engine uses floating-point atomics (marginals
+// over <= 11 wires: probs_marginal_kernel; the overlap accumulators of the fused adjoint passes: fusion.cu).
 #include <type_traits>
 
 #include "device.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace plb200 {
 
@@ -141,24 +140,67 @@ struct ProbsArgs {
     int k;
     int bits[40]; // output bit j (lsb-first) <- state bit bits[j]
 };
-// small k: shared-memory histogram per block, merged with fp64 atomics
+// small k: deterministic marginals.  A warp owns the elements that share the values of all target bits above the
+// lane bits and a chunk id over the non-target bits; its 32 lanes cover index bits 0-4 (one coalesced 512-byte access
+// per step), every lane sums its own elements in step order, lanes are combined by xor-shuffles over the lane bits
+// that are NOT targets, and each (outcome, chunk) partial is written by exactly one lane; probs_reduce_kernel adds an
+// outcome's chunks by a fixed tree.  No atomics anywhere: the same bits run after run.
+struct MargArgs {
+    int k;           // output bit j (lsb-first) <- state bit bits[j]
+    int bits[12];
+    int nlane;       // lane bits = index bits 0 .. nlane-1 (5, or n for tiny states)
+    int nhi;         // target bits above the lane bits, ascending: thi[]
+    int thi[12];
+    int nstep;       // non-target upper bits walked inside the warp (lowest ones), ascending: pstep[]
+    int pstep[8];
+    int nchunkbits;  // the remaining non-target upper bits: pchunk[] (ascending)
+    int pchunk[64];
+    unsigned lane_nontarget; // lane bits that are not targets
+};
 template <typename T2>
 __global__ void __launch_bounds__(kThreads)
-    probs_hist_kernel(const T2 *__restrict__ a, uint64_t len, double *out, const __grid_constant__ ProbsArgs p) {
-    extern __shared__ double hist[];
-    const int nout = 1 << p.k;
-    for (int i = threadIdx.x; i < nout; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const T2 x = a[i];
-        unsigned o = 0;
-        for (int j = 0; j < p.k; j++) o |= static_cast<unsigned>((i >> p.bits[j]) & 1) << j;
-        atomicAdd(&hist[o], static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y);
+    probs_marginal_kernel(const T2 *__restrict__ a, uint64_t nwarps, double *__restrict__ part, const __grid_constant__ MargArgs p) {
+    const uint64_t w = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    const uint64_t nchunks = uint64_t{1} << p.nchunkbits;
+    const uint64_t chunk = w & (nchunks - 1), ohi = w >> p.nchunkbits;
+    uint64_t base = 0;
+    for (int j = 0; j < p.nhi; j++) base |= ((ohi >> j) & 1) << p.thi[j];
+    for (int j = 0; j < p.nchunkbits; j++) base |= ((chunk >> j) & 1) << p.pchunk[j];
+    double s = 0;
+    if (lane < (1u << p.nlane)) {
+        for (unsigned st = 0; st < (1u << p.nstep); st++) {
+            uint64_t off = 0;
+            for (int j = 0; j < p.nstep; j++) off |= static_cast<uint64_t>((st >> j) & 1u) << p.pstep[j];
+            const T2 x = a[base | off | lane];
+            s += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+        }
     }
+    for (int b = 0; b < 5; b++)
+        if ((p.lane_nontarget >> b) & 1u) s += __shfl_xor_sync(0xffffffffu, s, 1 << b);
+    if ((lane & p.lane_nontarget) == 0 && lane < (1u << p.nlane)) {
+        const uint64_t idx = base | lane;
+        unsigned o = 0;
+        for (int j = 0; j < p.k; j++) o |= static_cast<unsigned>((idx >> p.bits[j]) & 1) << j;
+        part[static_cast<uint64_t>(o) * nchunks + chunk] = s;
+    }
+}
+// out[o] = sum of part[o * nchunks + c] over c, by a fixed tree (one block per outcome)
+__global__ void __launch_bounds__(256) probs_reduce_kernel(const double *__restrict__ part, uint64_t nchunks, double *__restrict__ out) {
+    __shared__ double sm[8];
+    const double *col = part + static_cast<uint64_t>(blockIdx.x) * nchunks;
+    double s = 0;
+    for (uint64_t c = threadIdx.x; c < nchunks; c += 256) s += col[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
     __syncthreads();
-    for (int i = threadIdx.x; i < nout; i += blockDim.x)
-        if (hist[i] != 0.0) atomicAdd(&out[i], hist[i]);
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += sm[w];
+        out[blockIdx.x] = t;
+    }
 }
 // large k: one thread per output, ordered sum over the remaining bits
 template <typename T2>
@@ -618,15 +660,31 @@ void probs_wires(StateVec &sv, const std::vector<int> &bits_msb_first, double *h
     double *dout;
     PLB_CUDA(cudaMalloc(&dout, nout * sizeof(double)));
     cudaError_t e = cudaSuccess;
+    double *dpart = nullptr;
     if (k <= 11) {
-        e = cudaMemsetAsync(dout, 0, nout * sizeof(double), sv.stream);
-        const int nb = reduce_blocks(sv, sv.length());
-        const size_t smem = nout * sizeof(double);
-        DISPATCH(sv,
-                 (probs_hist_kernel<T2><<<nb, kThreads, smem, sv.stream>>>(static_cast<const T2 *>(sv.data),
-                                                                           sv.length(), dout, p)),
-                 (probs_hist_kernel<T2><<<nb, kThreads, smem, sv.stream>>>(static_cast<const T2 *>(sv.data),
-                                                                           sv.length(), dout, p)));
+        MargArgs m;
+        std::memset(&m, 0, sizeof(m));
+        m.k = k;
+        for (int j = 0; j < k; j++) m.bits[j] = p.bits[j];
+        m.nlane = sv.n < 5 ? static_cast<int>(sv.n) : 5;
+        for (int b = 0; b < m.nlane; b++)
+            if (!(mmask >> b & 1)) m.lane_nontarget |= 1u << b;
+        for (int b = m.nlane; b < sv.n; b++) {
+            if (mmask >> b & 1) m.thi[m.nhi++] = b;
+            else if (m.nstep < 7) m.pstep[m.nstep++] = b;
+            else m.pchunk[m.nchunkbits++] = b;
+        }
+        const uint64_t nchunks = uint64_t{1} << m.nchunkbits;
+        const uint64_t nwarps = nchunks << m.nhi;
+        e = cudaMalloc(&dpart, nout * nchunks * sizeof(double));
+        if (e == cudaSuccess) {
+            const unsigned nb = static_cast<unsigned>((nwarps * 32 + kThreads - 1) / kThreads);
+            DISPATCH(sv,
+                     (probs_marginal_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), nwarps, dpart, m)),
+                     (probs_marginal_kernel<T2><<<nb, kThreads, 0, sv.stream>>>(static_cast<const T2 *>(sv.data), nwarps, dpart, m)));
+            probs_reduce_kernel<<<static_cast<unsigned>(nout), 256, 0, sv.stream>>>(dpart, nchunks, dout);
+            sv.launches++;
+        }
     } else {
         BitInsert ins;
         ins.n = 0;
@@ -645,6 +703,7 @@ void probs_wires(StateVec &sv, const std::vector<int> &bits_msb_first, double *h
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost, sv.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(sv.stream);
     cudaFree(dout);
+    if (dpart) cudaFree(dpart);
     PLB_CUDA(e);
 }
 

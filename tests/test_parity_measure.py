@@ -52,6 +52,35 @@ def test_probs_many_wires(plb, ref, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [2, 4, 5, 9, 20])
+def test_probs_marginals_deterministic(plb, dtype, n):
+    """Marginals over <= 11 wires (probs_marginal_kernel: one warp per (outcome, chunk), fixed-order sums, no
+    atomics): every kind of target placement — on the lane bits (last wires), above them, mixed, all wires of a
+    tiny state — against numpy on the gathered state, and bit-identical when repeated."""
+    a = plb.StateVector(n, dtype)
+    a.apply_ops(circuits.random_circuit(n, 3, 8) if n >= 2 else [], fuse=False)
+    psi = a.get_state().astype(np.complex128)
+    p_full = (np.abs(psi) ** 2).reshape((2,) * n)
+    rng = np.random.default_rng(n)
+    cases = [[n - 1], [0], list(range(n))[-min(n, 5):], list(range(min(n, 3))), [n - 1, 0]] if n > 1 else [[0]]
+    for _ in range(6):
+        k = int(rng.integers(1, min(n, 11) + 1))
+        cases.append([int(x) for x in rng.permutation(n)[:k]])
+    tol = 1e-13 if dtype == np.complex128 else 1e-6
+    for wires in cases:
+        if len(set(wires)) != len(wires) or len(wires) > 11:
+            continue
+        got = np.asarray(a.probs(wires))
+        rest = tuple(w for w in range(n) if w not in wires)
+        want = p_full.sum(axis=rest) if rest else p_full
+        # axes of `want` are the kept wires in ascending order: bring them into the caller's order
+        kept = sorted(wires)
+        want = np.transpose(want, [kept.index(w) for w in wires]).reshape(-1)
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=str(wires))
+        np.testing.assert_array_equal(np.asarray(a.probs(wires)), got)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_expval_var_named_and_matrix(plb, ref, dtype):
     n = 7
     a, b = _pair(plb, ref, n, dtype, 3)
