@@ -170,11 +170,20 @@ __global__ void __launch_bounds__(kThreads)
     for (int j = 0; j < p.nchunkbits; j++) base |= ((chunk >> j) & 1) << p.pchunk[j];
     double s = 0;
     if (lane < (1u << p.nlane)) {
-        for (unsigned st = 0; st < (1u << p.nstep); st++) {
-            uint64_t off = 0;
-            for (int j = 0; j < p.nstep; j++) off |= static_cast<uint64_t>((st >> j) & 1u) << p.pstep[j];
-            const T2 x = a[base | off | lane];
-            s += static_cast<double>(x.x) * x.x + static_cast<double>(x.y) * x.y;
+        // eight loads in flight per lane; the additions keep their order
+        for (unsigned st0 = 0; st0 < (1u << p.nstep); st0 += 8) {
+            T2 x[8];
+#pragma unroll
+            for (unsigned q = 0; q < 8; q++) {
+                const unsigned st = st0 + q;
+                uint64_t off = 0;
+#pragma unroll
+                for (int j = 0; j < 7; j++)
+                    if (j < p.nstep) off |= static_cast<uint64_t>((st >> j) & 1u) << p.pstep[j];
+                x[q] = st < (1u << p.nstep) ? a[base | off | lane] : T2{0, 0};
+            }
+#pragma unroll
+            for (unsigned q = 0; q < 8; q++) s += static_cast<double>(x[q].x) * x[q].x + static_cast<double>(x[q].y) * x[q].y;
         }
     }
     for (int b = 0; b < 5; b++)
