@@ -213,12 +213,15 @@ int plb200_emu_adjoint_schedule(int64_t n, int precision, const plb200_ops_t *op
 int plb200_emu_apply_ops(int64_t n, int precision, const plb200_ops_t *ops, void *state, int scaled, int64_t *stats4) {
     try {
         std::vector<AdjItem> items;
-        for (int64_t i = 0; i < ops->n_ops; i++)
-            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) {
+        for (int64_t i = 0; i < ops->n_ops; i++) {
+            std::vector<COp> pieces;
+            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces);
+            for (auto &lo : pieces) {
                 AdjItem it;
                 it.op = std::move(lo);
                 items.push_back(std::move(it));
             }
+        }
         double dummy = 0;
         Ctx ctx{static_cast<int>(n), precision, &items, state, nullptr, &dummy};
         // the stand-alone accumulators are added after emulate_fused zeroes its own
@@ -237,12 +240,15 @@ int plb200_emu_apply_ops_route(int64_t n, int precision, const plb200_ops_t *ops
                                const int64_t *lbits, int64_t my_value, void *const *dst, int *routed) {
     try {
         std::vector<AdjItem> items;
-        for (int64_t i = 0; i < ops->n_ops; i++)
-            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) {
+        for (int64_t i = 0; i < ops->n_ops; i++) {
+            std::vector<COp> pieces;
+            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces);
+            for (auto &lo : pieces) {
                 AdjItem it;
                 it.op = std::move(lo);
                 items.push_back(std::move(it));
             }
+        }
         RouteSpec rs;
         rs.k = static_cast<int>(k), rs.my_value = static_cast<int>(my_value);
         for (int64_t i = 0; i < k; i++) rs.lbits[i] = static_cast<int>(lbits[i]);

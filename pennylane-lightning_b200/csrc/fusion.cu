@@ -1058,8 +1058,18 @@ template <class Cfg, typename T2> size_t smem_bytes_for() {
 }
 
 std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
-    std::vector<AdjItem> items(ops.size());
-    for (size_t i = 0; i < ops.size(); i++) items[i].op = ops[i];
+    std::vector<AdjItem> items;
+    items.reserve(ops.size());
+    std::vector<COp> pieces;
+    for (const COp &o : ops) {
+        pieces.clear();
+        expand_for_fusion(o, pieces);
+        for (COp &q : pieces) {
+            AdjItem it;
+            it.op = std::move(q);
+            items.push_back(std::move(it));
+        }
+    }
     return items;
 }
 
@@ -1158,7 +1168,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
     build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
-        if (st.op >= 0) launch_op(sv, ops[st.op]);
+        if (st.op >= 0) launch_op(sv, items[st.op].op);
         else if (st.op == -2) scale(sv, st.scale);
         else {
             // the pass's specialised kernel when the cache has it (jit_runtime.cpp), else the interpreter
@@ -1217,7 +1227,7 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
     build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (have) launch_plain(held_st, *held), have = false; // the held pass was not the last step
-        if (st.op >= 0) launch_op(sv, ops[st.op]);
+        if (st.op >= 0) launch_op(sv, items[st.op].op);
         else if (st.op == -2) scale(sv, st.scale);
         else {
             // A pass in the specialised forms is held only when its plain kernel exists already (it may turn
@@ -1317,6 +1327,47 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
 
 } // namespace
 
+// A diagonal the tile encoder has no form for (a table over 2-4 bits that is not a parity form: the residual phases
+// of DoubleExcitationPlus / Minus, a diagonal QubitUnitary ...) is, when all but a few of its entries are equal,
+// a scalar on its control subspace times one controlled phase per exceptional entry — forms every pass can hold.
+// Everything else passes through unchanged.  Only the fused path sees the expansion.
+void expand_for_fusion(const COp &op, std::vector<COp> &out) {
+    const int k = op.k();
+    if (op.kind != OP_DIAG || op.parity || k < 2 || k > 4 || classify(op).fusable) {
+        out.push_back(op);
+        return;
+    }
+    const int D = 1 << k;
+    int best = 0, best_count = 0;
+    for (int i = 0; i < D; i++) {
+        int c = 0;
+        for (int j = 0; j < D; j++) c += op.diag[j] == op.diag[i];
+        if (c > best_count) best_count = c, best = i;
+    }
+    const cd v0 = op.diag[best];
+    if (D - best_count > 4 || v0 == cd(0.0)) {
+        out.push_back(op);
+        return;
+    }
+    uint64_t tmask = 0;
+    for (int b : op.tbits) tmask |= uint64_t{1} << b;
+    auto phase_op = [&](cd ph, uint64_t cmask, uint64_t cval) {
+        COp d;
+        d.kind = OP_DIAG;
+        d.cmask = cmask, d.cval = cval;
+        d.diag = {ph};
+        return d;
+    };
+    if (v0 != cd(1.0)) out.push_back(phase_op(v0, op.cmask, op.cval));
+    for (int i = 0; i < D; i++) {
+        if (op.diag[i] == v0) continue;
+        uint64_t pat = 0;
+        for (int j = 0; j < k; j++)
+            if ((i >> j) & 1) pat |= uint64_t{1} << op.tbits[j];
+        out.push_back(phase_op(op.diag[i] / v0, op.cmask | tmask, op.cval | pat));
+    }
+}
+
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
     const auto items = as_items(ops);
     out[0] = out[1] = out[2] = out[3] = 0;
@@ -1386,7 +1437,9 @@ bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const st
         if (tpi < 0) break;
         GateCall inv = c;
         inv.inverse = !c.inverse;
-        for (auto &lo : lower_gate(n, inv)) {
+        std::vector<COp> pieces;
+        for (auto &lo : lower_gate(n, inv)) expand_for_fusion(lo, pieces);
+        for (auto &lo : pieces) {
             AdjItem it;
             it.op = std::move(lo);
             items.push_back(std::move(it));

@@ -9,6 +9,10 @@ namespace plb200 {
 // Applies `ops` in order with as few HBM sweeps as the scheduler finds; arithmetic per gate is
 // identical to launch_ops().
 void run_fused(StateVec &sv, const std::vector<COp> &ops);
+// What the fused path schedules instead of `op`: the op itself, or — for a diagonal the tile encoder has no form
+// for whose entries are all equal but a few — a scalar on its control subspace and one controlled phase per
+// exceptional entry (appended to `out`).
+void expand_for_fusion(const COp &op, std::vector<COp> &out);
 // Host-only: out = {tile passes, stand-alone kernels, rounds, ops executed inside tile passes}
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]);
 

@@ -539,3 +539,50 @@ def test_two_wire_unitaries_fused_on_device(plb, ref, jit_sync, dtype):
     r = ref.StateVector(n, dtype)
     r.apply_ops(ops)
     np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=2 * TOL[np.dtype(dtype)])
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_non_parity_diagonals_expand_into_controlled_phases(plb, dtype, monkeypatch):
+    """fusion.cu expand_for_fusion: the residual 16-entry diagonal of DoubleExcitationPlus / Minus and diagonal
+    QubitUnitaries whose entries are all equal but a few become a scalar + controlled phases, which every pass can
+    hold — with pair ops fused nothing of such a tape runs stand-alone; both through the generated code and through
+    the interpreter (refused passes)."""
+    from test_tile_emulation import emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "1")
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 14
+    rng = np.random.default_rng(31)
+    ops = []
+    for _ in range(70):
+        r = rng.random()
+        w = [int(x) for x in rng.permutation(n)[:5]]
+        if r < 0.35:
+            ops.append(circuits.op(("RX", "RY", "RZ", "Hadamard")[int(rng.integers(4))], w[:1], [rng.uniform(0, 6)]))
+            if ops[-1]["name"] == "Hadamard":
+                ops[-1]["params"] = []
+        elif r < 0.6:
+            ops.append(circuits.op(("DoubleExcitationPlus", "DoubleExcitationMinus")[int(rng.integers(2))], w[:4],
+                                   [rng.uniform(0, 6)], inverse=bool(rng.integers(2)),
+                                   ctrl_wires=w[4:5] if rng.random() < 0.3 else [],
+                                   ctrl_values=[True] if False else []))
+            ops[-1]["ctrl_values"] = [bool(rng.integers(2))] * len(ops[-1]["ctrl_wires"])
+        elif r < 0.8:  # diagonal unitary on 2 or 3 wires with one or two exceptional entries
+            k = int(rng.integers(2, 4))
+            d = np.full(1 << k, np.exp(1j * rng.uniform(0, 6)))
+            for i in rng.permutation(1 << k)[: int(rng.integers(1, 3))]:
+                d[i] = np.exp(1j * rng.uniform(0, 6))
+            o = circuits.op("QubitUnitary", w[:k], [], inverse=bool(rng.integers(2)))
+            o["matrix"] = np.diag(d)
+            ops.append(o)
+        else:
+            ops.append(circuits.op("CNOT", w[:2]))
+    st = random_state(n, dtype, 2)
+    expect = oracle_apply(n, ops, st)
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    assert stats[1] == 0 and stats[0] >= 1, stats
+    np.testing.assert_allclose(out, expect, rtol=0, atol=2 * TOL[np.dtype(dtype)])
+    monkeypatch.setenv("PLB200_EMU_REFUSE", "1")
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    np.testing.assert_allclose(out, expect, rtol=0, atol=2 * TOL[np.dtype(dtype)])
