@@ -586,3 +586,38 @@ def test_non_parity_diagonals_expand_into_controlled_phases(plb, dtype, monkeypa
     monkeypatch.setenv("PLB200_EMU_REFUSE", "1")
     out, stats = emu_apply(emu, plb, n, ops, st, True)
     np.testing.assert_allclose(out, expect, rtol=0, atol=2 * TOL[np.dtype(dtype)])
+
+
+@pytest.mark.gpu
+def test_excitation_variants_and_diagonal_unitaries_fused_on_device(plb, ref, jit_sync):
+    """DoubleExcitationPlus / Minus (K_PAIR4 + expanded residual phases) and nearly-uniform diagonal unitaries inside
+    specialised passes against lightning.qubit: no stand-alone kernel."""
+    n = 17
+    rng = np.random.default_rng(41)
+    ops = []
+    for _ in range(80):
+        r = rng.random()
+        w = [int(x) for x in rng.permutation(n)[:5]]
+        if r < 0.4:
+            ops.append(circuits.op(("RX", "RY", "RZ")[int(rng.integers(3))], w[:1], [rng.uniform(0, 6)]))
+        elif r < 0.65:
+            ops.append(circuits.op(("DoubleExcitationPlus", "DoubleExcitationMinus", "DoubleExcitation")[int(rng.integers(3))],
+                                   w[:4], [rng.uniform(0, 6)], inverse=bool(rng.integers(2))))
+        elif r < 0.8:
+            d = np.full(8, np.exp(1j * rng.uniform(0, 6)))
+            d[int(rng.integers(8))] = np.exp(1j * rng.uniform(0, 6))
+            o = circuits.op("QubitUnitary", w[:3], [])
+            o["matrix"] = np.diag(d)
+            ops.append(o)
+        else:
+            ops.append(circuits.op("CNOT", w[:2]))
+    blob = plb.OpsBlob(ops)
+    sched = (C.c_int64 * 4)()
+    assert plb.lib().plb200_schedule_stats(C.c_int64(n), 64, blob.ptr(), sched) == 0
+    assert sched[1] == 0, list(sched)
+    a = plb.StateVector(n)
+    a.apply_ops(blob, fuse=True)
+    assert a.last_apply_stats()[1] == sched[0]
+    r_ = ref.StateVector(n)
+    r_.apply_ops(ops)
+    np.testing.assert_allclose(a.get_state(), r_.get_state(), rtol=0, atol=1e-12)
