@@ -215,7 +215,7 @@ int plb200_emu_apply_ops(int64_t n, int precision, const plb200_ops_t *ops, void
         std::vector<AdjItem> items;
         for (int64_t i = 0; i < ops->n_ops; i++) {
             std::vector<COp> pieces;
-            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces);
+            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces, n >= (precision == 64 ? 12 : 14));
             for (auto &lo : pieces) {
                 AdjItem it;
                 it.op = std::move(lo);
@@ -242,7 +242,7 @@ int plb200_emu_apply_ops_route(int64_t n, int precision, const plb200_ops_t *ops
         std::vector<AdjItem> items;
         for (int64_t i = 0; i < ops->n_ops; i++) {
             std::vector<COp> pieces;
-            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces);
+            for (auto &lo : lower_gate(n, call_from_blob(*ops, i))) expand_for_fusion(lo, pieces, n >= (precision == 64 ? 12 : 14));
             for (auto &lo : pieces) {
                 AdjItem it;
                 it.op = std::move(lo);

@@ -1057,13 +1057,14 @@ template <class Cfg, typename T2> size_t smem_bytes_for() {
            (Cfg::NS == 2 ? sizeof(double) * kMaxPassOps * ((1u << (Cfg::M - Cfg::R)) / 32) : 0); // one accumulator row per warp
 }
 
-std::vector<AdjItem> as_items(const std::vector<COp> &ops) {
+// tiles: the state is large enough for tile passes (multi-op expansions pay only then)
+std::vector<AdjItem> as_items(const std::vector<COp> &ops, bool tiles = true) {
     std::vector<AdjItem> items;
     items.reserve(ops.size());
     std::vector<COp> pieces;
     for (const COp &o : ops) {
         pieces.clear();
-        expand_for_fusion(o, pieces);
+        expand_for_fusion(o, pieces, tiles);
         for (COp &q : pieces) {
             AdjItem it;
             it.op = std::move(q);
@@ -1155,7 +1156,7 @@ void launch_pass(const Step &st, cudaStream_t stream, T2 *sv0, T2 *sv1, double *
 // is a by-value kernel parameter), so the host schedules pass k+1 while the GPU runs pass k.
 template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp> &ops) {
     using Cfg = FwdCfg<T2>;
-    const auto items = as_items(ops);
+    const auto items = as_items(ops, sv.n >= Cfg::M + 1);
     prepare_kernel<T2, Cfg>(sv.device);
     // PLB200_FUSE_TRACE=1: per-step device time on stderr (profiling aid; serialises the steps)
     const bool trace = std::getenv("PLB200_FUSE_TRACE") != nullptr;
@@ -1207,7 +1208,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
 // schedule, last round not line-coalesced, NVRTC missing): the caller then swaps with the stand-alone kernel.
 template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec &rs) {
     using Cfg = FwdCfg<T2>;
-    const auto items = as_items(ops);
+    const auto items = as_items(ops, sv.n >= Cfg::M + 1);
     prepare_kernel<T2, Cfg>(sv.device);
     const bool use_jit = jit::mode() != jit::Mode::Off && sv.n >= jit::min_qubits();
     const unsigned nt = 1u << (Cfg::M - Cfg::R);
@@ -1331,7 +1332,53 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
 // of DoubleExcitationPlus / Minus, a diagonal QubitUnitary ...) is, when all but a few of its entries are equal,
 // a scalar on its control subspace times one controlled phase per exceptional entry — forms every pass can hold.
 // Everything else passes through unchanged.  Only the fused path sees the expansion.
-void expand_for_fusion(const COp &op, std::vector<COp> &out) {
+void expand_for_fusion(const COp &op, std::vector<COp> &out, bool tiles) {
+    if (tiles && op.kind == OP_PAIRS && op.parity && op.cmask == 0 && op.blocks.size() == 1 && !op.tbits.empty()) {
+        // exp(-i theta/2 P) for a Pauli word with X / Y letters (lower_pauli_rot's parity-paired form):
+        // = U exp(-i theta/2 Z...Z) U^+ with U = H on the X wires and S H on the Y wires — single-bit pair ops and
+        // a parity diagonal, which tile passes hold, instead of a sweep of its own.
+        uint64_t x = 0;
+        for (int b : op.tbits) x |= uint64_t{1} << b;
+        const uint64_t z = op.pmask;
+        const int ny = __builtin_popcountll(x & z);
+        cd iy = 1.0;
+        for (int q = 0; q < (ny & 3); q++) iy *= cd(0.0, 1.0);
+        const double c = op.blocks[0].m[0].real();
+        const double sn = (op.blocks[0].m[1] / (cd(0.0, -1.0) * iy)).real(); // m[1] = -i s i^ny
+        const double r = 0.70710678118654752440;
+        auto had = [&](int bit) {
+            COp h;
+            h.kind = OP_PAIRS;
+            h.tbits = {bit};
+            Block2 bl;
+            bl.a = 0, bl.b = 1;
+            bl.m[0] = r, bl.m[1] = r, bl.m[2] = r, bl.m[3] = -r;
+            h.blocks.push_back(bl);
+            return h;
+        };
+        auto sgate = [&](int bit, bool dagger) {
+            COp d;
+            d.kind = OP_DIAG;
+            d.tbits = {bit};
+            d.diag = {cd(1.0), cd(0.0, dagger ? -1.0 : 1.0)};
+            return d;
+        };
+        for (int b : op.tbits) {
+            if (z >> b & 1) out.push_back(sgate(b, true));
+            out.push_back(had(b));
+        }
+        COp d;
+        d.kind = OP_DIAG;
+        d.parity = true;
+        d.pmask = x | z;
+        d.pd[0] = cd(c, -sn), d.pd[1] = cd(c, sn);
+        out.push_back(d);
+        for (int b : op.tbits) {
+            out.push_back(had(b));
+            if (z >> b & 1) out.push_back(sgate(b, false));
+        }
+        return;
+    }
     const int k = op.k();
     if (op.kind != OP_DIAG || op.parity || k < 2 || k > 4 || classify(op).fusable) {
         out.push_back(op);
@@ -1369,7 +1416,7 @@ void expand_for_fusion(const COp &op, std::vector<COp> &out) {
 }
 
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]) {
-    const auto items = as_items(ops);
+    const auto items = as_items(ops, n >= (precision == 64 ? FwdCfg<double2>::M : FwdCfg<float2>::M) + 1);
     out[0] = out[1] = out[2] = out[3] = 0;
     auto count = [&](const Step &s, const void *) {
         if (s.op >= 0) out[1]++;
@@ -1381,7 +1428,7 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
 
 // Host-only: the specialised source of every tile pass of the tape (tools, tests, compile-time checks).
 void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector<std::string> &out) {
-    const auto items = as_items(ops);
+    const auto items = as_items(ops, n >= (precision == 64 ? FwdCfg<double2>::M : FwdCfg<float2>::M) + 1);
     const char *jfe = std::getenv("PLB200_JIT_FORMS");
     const bool jit_forms = !(jfe && jfe[0] == '0'); // what the specialised tier compiles
     // PLB200_DUMP_REFUSE=1 (tests): every pass in the specialised forms is refused after its source was taken, as
@@ -1438,7 +1485,7 @@ bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const st
         GateCall inv = c;
         inv.inverse = !c.inverse;
         std::vector<COp> pieces;
-        for (auto &lo : lower_gate(n, inv)) expand_for_fusion(lo, pieces);
+        for (auto &lo : lower_gate(n, inv)) expand_for_fusion(lo, pieces, n >= 13);
         for (auto &lo : pieces) {
             AdjItem it;
             it.op = std::move(lo);

@@ -11,8 +11,9 @@ namespace plb200 {
 void run_fused(StateVec &sv, const std::vector<COp> &ops);
 // What the fused path schedules instead of `op`: the op itself, or — for a diagonal the tile encoder has no form
 // for whose entries are all equal but a few — a scalar on its control subspace and one controlled phase per
-// exceptional entry (appended to `out`).
-void expand_for_fusion(const COp &op, std::vector<COp> &out);
+// exceptional entry; for a Pauli rotation with X / Y letters — when `tiles` says the state is large enough for tile
+// passes — basis changes (H, S) around a parity diagonal (appended to `out`).
+void expand_for_fusion(const COp &op, std::vector<COp> &out, bool tiles = true);
 // Host-only: out = {tile passes, stand-alone kernels, rounds, ops executed inside tile passes}
 void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t out[4]);
 

@@ -621,3 +621,80 @@ def test_excitation_variants_and_diagonal_unitaries_fused_on_device(plb, ref, ji
     r_ = ref.StateVector(n)
     r_.apply_ops(ops)
     np.testing.assert_allclose(a.get_state(), r_.get_state(), rtol=0, atol=1e-12)
+
+
+def _pauli_rot_tape(n, seed, count=60):
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(count):
+        r = rng.random()
+        w = [int(x) for x in rng.permutation(n)[:4]]
+        if r < 0.45:
+            k = int(rng.integers(1, 5))
+            word = "".join("XYZ"[int(rng.integers(3))] for _ in range(k))
+            ops.append(circuits.op(f"PauliRot[{word}]", w[:k], [rng.uniform(0, 6)], inverse=bool(rng.integers(2))))
+        elif r < 0.8:
+            ops.append(circuits.op(("RX", "RY", "RZ")[int(rng.integers(3))], w[:1], [rng.uniform(0, 6)]))
+        else:
+            ops.append(circuits.op("CNOT", w[:2]))
+    return ops
+
+
+def _apply_with_pauli_rot(n, ops, state):
+    from oracle import np_oracle
+
+    sv = np_oracle.StateVector(n, np.complex128)
+    sv.set_state(state.astype(np.complex128))
+    for o in ops:
+        if o["name"].startswith("PauliRot["):
+            sv.apply_pauli_rot(o["wires"], o["inverse"], o["params"][0], o["name"][9:-1])
+        else:
+            sv.apply_ops([o])
+    return sv.get_state()
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("specialised", [False, True])
+def test_pauli_rotations_fused_through_basis_changes(plb, dtype, specialised, monkeypatch):
+    """fusion.cu expand_for_fusion: exp(-i theta/2 P) with X / Y letters runs inside tile passes as H / S basis
+    changes around a parity diagonal — nothing stand-alone — and gives GateImplementationsLM.hpp:575-629's state
+    (the oracle's apply_pauli_rot), through the interpreter and through the generated code."""
+    from test_tile_emulation import emu_apply
+
+    emu = _emu_lib()
+    if specialised:
+        monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    n = 14
+    ops = _pauli_rot_tape(n, 6)
+    st = random_state(n, dtype, 3)
+    out, stats = emu_apply(emu, plb, n, ops, st, True)
+    assert stats[1] == 0 and stats[0] >= 1, stats
+    np.testing.assert_allclose(out, _apply_with_pauli_rot(n, ops, st), rtol=0, atol=2 * TOL[np.dtype(dtype)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["interpreter", "specialised"])
+def test_pauli_rotations_fused_on_device(plb, ref, mode, monkeypatch):
+    """Pauli rotations with X / Y letters inside a tape: no stand-alone kernel (basis changes + a parity diagonal
+    inside the tile passes), lightning.qubit's applyPauliRot state."""
+    monkeypatch.setenv("PLB200_JIT_MIN_QUBITS", "12")
+    plb.jit_set_mode(2 if mode == "specialised" else 0)
+    try:
+        n = 17
+        ops = _pauli_rot_tape(n, 9, 80)
+        blob = plb.OpsBlob(ops)
+        sched = (C.c_int64 * 4)()
+        assert plb.lib().plb200_schedule_stats(C.c_int64(n), 64, blob.ptr(), sched) == 0
+        assert sched[1] == 0, list(sched)
+        a = plb.StateVector(n)
+        a.apply_ops(blob, fuse=True)
+        assert a.last_apply_stats()[1] == sched[0]
+        r = ref.StateVector(n)
+        for o in ops:
+            if o["name"].startswith("PauliRot["):
+                r.apply_pauli_rot(o["wires"], o["inverse"], o["params"][0], o["name"][9:-1])
+            else:
+                r.apply_ops([o])
+        np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=1e-12)
+    finally:
+        plb.jit_set_mode(-1)
