@@ -1007,7 +1007,7 @@ int plb200_adjoint_jacobian(const plb200_sv *sv, const plb200_obs *const *obs, i
         if (fuse_ok) {
             std::vector<double> acc(n_tp, 0.0);
             int64_t st[3];
-            run_adjoint_fused(lambda.s, hl[0]->s, items, static_cast<int>(n_tp), acc.data(), st);
+            run_adjoint_fused(lambda.s, hl[0]->s, items, static_cast<int>(n_tp), acc.data(), st, &const_cast<StateVec &>(ref));
             for (int64_t p = 0; p < n_tp; p++) jac[p] = -2.0 * sfs[p] * acc[p];
             const_cast<StateVec &>(ref).launches += lambda.s.launches + hl[0]->s.launches;
             const_cast<StateVec &>(ref).last_stats[0] = st[0], const_cast<StateVec &>(ref).last_stats[1] = st[1];

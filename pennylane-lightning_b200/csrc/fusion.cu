@@ -1258,7 +1258,7 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
 
 template <typename T2>
 void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
-                       double *acc_host, int64_t stats[3]) {
+                       double *acc_host, int64_t stats[3], StateVec &scratch) {
     using Cfg = AdjCfg<T2>;
     for (int i = 0; i < n_slots; i++) acc_host[i] = 0.0;
     prepare_kernel<T2, Cfg>(lambda.device);
@@ -1267,9 +1267,12 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
     const size_t max_pass = items.size() / 2 + 1;
     const size_t acc_bytes = max_pass * kMaxPassOps * sizeof(double);
     // + the per-CTA partials of the pass in flight (reduced in CTA order right after it: deterministic)
-    const size_t max_grid = static_cast<size_t>(lambda.sm_count) * 3 * 64;
-    const size_t part_bytes = max_grid * kMaxPassOps * sizeof(double);
-    double *dacc = static_cast<double *>(lambda.plan_buf(acc_bytes + part_bytes));
+    // (the buffers live with `scratch` — the caller's persistent state — so that a Jacobian per optimiser step
+    // does not pay a cudaMalloc / cudaFree of tens of megabytes each time)
+    const size_t max_grid = static_cast<size_t>(std::min<uint64_t>(uint64_t{1} << (lambda.n > Cfg::M ? lambda.n - Cfg::M : 0),
+                                                                   uint64_t(lambda.sm_count) * 3 * 64));
+    const size_t part_bytes = max_grid * static_cast<size_t>(std::min<int>(kMaxPassOps, std::max(1, n_slots))) * sizeof(double);
+    double *dacc = static_cast<double *>(scratch.plan_buf(acc_bytes + part_bytes));
     double *dpart = dacc + max_pass * kMaxPassOps;
     PLB_CUDA(cudaMemsetAsync(dacc, 0, acc_bytes, lambda.stream));
     struct PassSlots {
@@ -1513,11 +1516,12 @@ bool run_fused_routed(StateVec &sv, const std::vector<COp> &ops, const RouteSpec
 }
 
 void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
-                       double *acc_host, int64_t stats[3]) {
+                       double *acc_host, int64_t stats[3], StateVec *scratch) {
     lambda.set_device();
     stats[0] = stats[1] = stats[2] = 0;
-    if (lambda.precision == 64) run_adjoint_typed<double2>(lambda, hl, items, n_slots, acc_host, stats);
-    else run_adjoint_typed<float2>(lambda, hl, items, n_slots, acc_host, stats);
+    StateVec &owner = scratch ? *scratch : lambda;
+    if (lambda.precision == 64) run_adjoint_typed<double2>(lambda, hl, items, n_slots, acc_host, stats, owner);
+    else run_adjoint_typed<float2>(lambda, hl, items, n_slots, acc_host, stats, owner);
 }
 #else
 // ------------------------------------------------------------------------------------------

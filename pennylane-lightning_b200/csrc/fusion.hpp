@@ -49,6 +49,7 @@ bool build_adjoint_items(int64_t n, const std::vector<GateCall> &calls, const st
                          int64_t num_param_ops, std::vector<AdjItem> &items, std::vector<double> &sfs);
 // Runs the items in order on the pair (lambda, H lambda) with tile passes over both states;
 // acc_host[slot] receives Im<H lambda|P|lambda>.  stats = {tile passes, stand-alone items, fused items}.
+// scratch: the state whose plan buffer holds the accumulators (a persistent one saves an allocation per call).
 void run_adjoint_fused(StateVec &lambda, StateVec &hl, const std::vector<AdjItem> &items, int n_slots,
-                       double *acc_host, int64_t stats[3]);
+                       double *acc_host, int64_t stats[3], StateVec *scratch = nullptr);
 } // namespace plb200
