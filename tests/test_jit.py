@@ -698,3 +698,52 @@ def test_pauli_rotations_fused_on_device(plb, ref, mode, monkeypatch):
         np.testing.assert_allclose(a.get_state(), r.get_state(), rtol=0, atol=1e-12)
     finally:
         plb.jit_set_mode(-1)
+
+
+def test_fuzz_generated_code_all_forms(plb, monkeypatch):
+    """Random tapes over the whole gate set — plus DoubleExcitation(+-), two-wire unitaries, nearly-uniform diagonal
+    unitaries — through the encoder's jit forms and the g++-compiled generated code, with pair ops fused
+    (PLB200_FUSE_PAIR2=1); every third tape with all such passes refused (interpreter pieces + stand-alone pair ops).
+    Amplitudes against the oracle."""
+    from test_tile_emulation import _fuzz_tape, emu_apply, oracle_apply
+
+    emu = _emu_lib()
+    monkeypatch.setenv("PLB200_FUSE_PAIR2", "1")
+    monkeypatch.setenv("PLB200_EMU_JIT", "1")
+    for seed in range(12):
+        rng = np.random.default_rng(7000 + seed)
+        n = int(rng.integers(12, 15)) + (seed % 2) * 2  # c64 tiles need 14 qubits
+        dtype = [np.complex128, np.complex64][seed % 2]
+        ops = _fuzz_tape(n, rng, int(rng.integers(60, 160)), "ladder" if seed % 6 == 5 else "mixed")
+        extra = []
+        for _ in range(int(rng.integers(3, 10))):
+            w = [int(x) for x in rng.permutation(n)[:5]]
+            r = rng.random()
+            if r < 0.4:
+                nm = ("DoubleExcitation", "DoubleExcitationPlus", "DoubleExcitationMinus")[int(rng.integers(3))]
+                extra.append(circuits.op(nm, w[:4], [rng.uniform(0, 6)], inverse=bool(rng.integers(2))))
+            elif r < 0.7:
+                a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+                q, rr = np.linalg.qr(a)
+                o = circuits.op("QubitUnitary", w[:2], [], inverse=bool(rng.integers(2)),
+                                ctrl_wires=w[2:3] if rng.random() < 0.3 else [])
+                o["ctrl_values"] = [bool(rng.integers(2))] * len(o["ctrl_wires"])
+                o["matrix"] = q * (np.diag(rr) / np.abs(np.diag(rr)))
+                extra.append(o)
+            else:
+                d = np.full(8, np.exp(1j * rng.uniform(0, 6)))
+                d[int(rng.integers(8))] = np.exp(1j * rng.uniform(0, 6))
+                o = circuits.op("QubitUnitary", w[:3], [])
+                o["matrix"] = np.diag(d)
+                extra.append(o)
+        for o in extra:
+            ops.insert(int(rng.integers(len(ops) + 1)), o)
+        if seed % 3 == 2:
+            monkeypatch.setenv("PLB200_EMU_REFUSE", "1")
+        else:
+            monkeypatch.delenv("PLB200_EMU_REFUSE", raising=False)
+        st = random_state(n, dtype, seed)
+        out, stats = emu_apply(emu, plb, n, ops, st)
+        tol = 5e-12 if dtype == np.complex128 else 3e-4
+        err = float(np.max(np.abs(out - oracle_apply(n, ops, st))))
+        assert err < tol, (seed, n, len(ops), err, stats)
