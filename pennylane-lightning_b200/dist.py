@@ -755,6 +755,34 @@ class DistStateVector:
                       ctrl_wires=[], ctrl_values=[]) for c, w in zip(word, wires) if c != "I"]
         self.apply_ops(gates, fuse=False)
 
+    def _apply_hamiltonian(self, coeffs, words, wires, scratch, followers=()):
+        """H|self> for H = sum_k c_k P_k as a new sharded vector on self's wire map.  `scratch` (a clone) holds one
+        term at a time; `followers` are vectors that must stay on the same map: every exchange this needs (X / Y
+        letters on global wires) is made on all of them."""
+        out = self.clone(copy_state=False)
+        for c, word, ws in zip(coeffs, words, wires):
+            xy = [w for ch, w in zip(word, ws) if ch in "XY"]
+            for v in [self] + list(followers) + [out]:  # same call on every vector: the maps stay equal
+                v._make_wires_local(xy)
+            scratch._assign(self)
+            scratch._apply_pauli_word(word, ws)
+            assert scratch.phys == out.phys == self.phys
+            out.engine.axpy(complex(c), scratch.engine)
+        return out
+
+    def var_pauli_hamiltonian(self, coeffs, words, wires):
+        """Variance <H^2> - <H>^2 of H = sum_k c_k P_k on the sharded state (MeasurementsGPUMPI::var for a
+        Hamiltonian: ||H psi||^2 - <psi|H psi>^2 with H psi built slab by slab).  The state's wire map may change
+        (exchanges for X / Y letters on global wires); its amplitudes do not."""
+        scratch = self.clone(copy_state=False)
+        hpsi = self._apply_hamiltonian(coeffs, words, wires, scratch)
+        h2 = hpsi.inner(hpsi).real
+        h1 = self.inner(hpsi).real
+        nrm = self.inner(self).real
+        for v in (scratch, hpsi):
+            v.close()
+        return h2 / nrm - (h1 / nrm) ** 2
+
     def adjoint_jacobian(self, ops, trainable_params, observables):
         """Jacobian d<H_j>/d theta_p of the tape `ops` from |0...0>, for Hamiltonians of Pauli words
         `observables` = [(coeffs, words, wires), ...] and the trainable parameter indices `trainable_params`
@@ -778,16 +806,7 @@ class DistStateVector:
         mu = lam.clone(copy_state=False)
         hls = []
         for coeffs, words, wires in observables:
-            hl = lam.clone(copy_state=False)
-            for c, word, ws in zip(coeffs, words, wires):
-                xy = [w for ch, w in zip(word, ws) if ch in "XY"]
-                for v in [lam] + hls + [hl]:  # same call on every vector: the maps stay equal
-                    v._make_wires_local(xy)
-                mu._assign(lam)
-                mu._apply_pauli_word(word, ws)
-                assert mu.phys == hl.phys == lam.phys
-                hl.engine.axpy(complex(c), mu.engine)
-            hls.append(hl)
+            hls.append(lam._apply_hamiltonian(coeffs, words, wires, mu, hls))
         jac = np.zeros((len(observables), len(tp)))
         tpi, cur = len(tp) - 1, n_par_ops - 1
         for o in reversed(ops):

@@ -247,9 +247,10 @@ def worker_measure(rank, world, n, seed, port, backend, q):
         p_all = sv.probs()
         samples = sv.generate_samples(4000, seed=11)
         samples2 = sv.generate_samples(4000, seed=11)
+        var = sv.var_pauli_hamiltonian(co, words, wires)
         full = sv.gather_state()
         if rank == 0:
-            q.put(dict(each=each, total=total, pw=pw, p_sub=p_sub, p_all=p_all, samples=samples,
+            q.put(dict(each=each, total=total, pw=pw, p_sub=p_sub, p_all=p_all, samples=samples, var=var,
                        same=bool(np.array_equal(samples, samples2)), state=full, words=words, wires=wires, co=co))
     finally:
         dist.destroy_process_group()
@@ -264,6 +265,16 @@ def check_measurements(res, n):
     for k, (w, ws) in enumerate(zip(res["words"], res["wires"])):
         assert abs(res["each"][k] - ref.expval_pauli_word(w, ws)) < 1e-12
     assert abs(res["total"] - sum(c * ref.expval_pauli_word(w, ws) for c, w, ws in zip(res["co"], res["words"], res["wires"]))) < 1e-12
+    # variance of the Hamiltonian: ||H psi||^2 - <H>^2 with H psi from the oracle's Pauli-word application
+    hpsi = np.zeros_like(psi, dtype=np.complex128)
+    for c, w, ws in zip(res["co"], res["words"], res["wires"]):
+        t = np_oracle.StateVector(n)
+        t.set_state(psi)
+        t.apply_ops([dict(name={"X": "PauliX", "Y": "PauliY", "Z": "PauliZ"}[ch], wires=[q], params=[], inverse=False,
+                          ctrl_wires=[], ctrl_values=[]) for ch, q in zip(w, ws)])
+        hpsi += c * t.get_state()
+    want_var = float(np.vdot(hpsi, hpsi).real - np.vdot(psi, hpsi).real ** 2)
+    assert abs(res["var"] - want_var) < 1e-11, (res["var"], want_var)
     np.testing.assert_allclose(res["p_sub"], ref.probs(res["pw"]), rtol=0, atol=1e-13)
     np.testing.assert_allclose(res["p_all"], ref.probs(), rtol=0, atol=1e-13)
     s = res["samples"]
