@@ -236,6 +236,10 @@ class LocalEngine:
         """un-normalised <slab| P_k |slab> for Pauli words over LOCAL wires (engine wire numbering)"""
         return np.asarray(self.sv.expval_pauli_words_each(words, local_wires))
 
+    def matrix_sum(self, matrix, local_wires):
+        """un-normalised <slab| M |slab> for a matrix on LOCAL wires"""
+        return self.sv.expval_matrix(matrix, local_wires)
+
     def probs(self, local_wires=None):
         """un-normalised |a_i|^2 marginal over the given local wires (all local wires when None)"""
         return self.sv.probs(local_wires)
@@ -676,6 +680,17 @@ class DistStateVector:
         self.last_norm2 = float(out[len(words)])
         vals = out[: len(words)]
         return float(np.dot(coeffs, vals)) if coeffs is not None else vals
+
+    def expval_matrix(self, matrix, wires):
+        """<psi| M |psi> for a Hermitian matrix on `wires` (MeasurementsGPUMPI::expval(matrix, wires)): the wires are
+        made local (one exchange at most), every rank evaluates its slab, one all_reduce."""
+        wires = list(wires)
+        self._make_wires_local(wires)
+        loc = self.engine.matrix_sum(np.asarray(matrix, dtype=np.complex128), [self._lw(w) for w in wires])
+        nrm = self.engine.pauli_sums(["I"], [[0]])[0]
+        out = self._allreduce([loc, nrm])
+        self.last_norm2 = float(out[1])
+        return float(out[0] / out[1])
 
     def probs(self, wires=None):
         """Marginal probabilities over `wires` (all wires when None), ordered by the given wire order

@@ -57,6 +57,9 @@ class NumpyEngine:
         return np.array([self.sv.expval_pauli_word(w, ws) if w.strip("I") else float(np.vdot(self.sv.state, self.sv.state).real)
                          for w, ws in zip(words, local_wires)])
 
+    def matrix_sum(self, matrix, local_wires):
+        return self.sv.expval_matrix(matrix, local_wires)
+
     def probs(self, local_wires=None):
         return self.sv.probs(local_wires)
 
@@ -248,9 +251,14 @@ def worker_measure(rank, world, n, seed, port, backend, q):
         samples = sv.generate_samples(4000, seed=11)
         samples2 = sv.generate_samples(4000, seed=11)
         var = sv.var_pauli_hamiltonian(co, words, wires)
+        rngm = np.random.default_rng(seed + 5)
+        mw = [int(x) for x in rngm.permutation(n)[:2]]
+        hm = rngm.normal(size=(4, 4)) + 1j * rngm.normal(size=(4, 4))
+        hm = hm + hm.conj().T
+        em = sv.expval_matrix(hm, mw)
         full = sv.gather_state()
         if rank == 0:
-            q.put(dict(each=each, total=total, pw=pw, p_sub=p_sub, p_all=p_all, samples=samples, var=var,
+            q.put(dict(each=each, total=total, pw=pw, p_sub=p_sub, p_all=p_all, samples=samples, var=var, em=em, hm=hm, mw=mw,
                        same=bool(np.array_equal(samples, samples2)), state=full, words=words, wires=wires, co=co))
     finally:
         dist.destroy_process_group()
@@ -275,6 +283,7 @@ def check_measurements(res, n):
         hpsi += c * t.get_state()
     want_var = float(np.vdot(hpsi, hpsi).real - np.vdot(psi, hpsi).real ** 2)
     assert abs(res["var"] - want_var) < 1e-11, (res["var"], want_var)
+    assert abs(res["em"] - ref.expval_matrix(res["hm"], res["mw"])) < 1e-11
     np.testing.assert_allclose(res["p_sub"], ref.probs(res["pw"]), rtol=0, atol=1e-13)
     np.testing.assert_allclose(res["p_all"], ref.probs(), rtol=0, atol=1e-13)
     s = res["samples"]
