@@ -469,7 +469,10 @@ PairForm pair_form(const cd *min, bool fold, bool jf = false, double max_growth 
 // pass is encoded again in the interpreter's forms and handed over a second time.  The schedule itself (tiles,
 // rounds, order) is the same either way; only the records and the host-carried scalar differ.
 template <typename T2, class Cfg, class OnStep>
-void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled, bool jit_forms, OnStep &&on_step) {
+void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool allow_scaled, int forms, OnStep &&on_step) {
+    // forms: 0 = no kernel will ever be compiled from these passes (interpreter only: the scalar slot exists only
+    // where the scalar is folded back); 1 = kernels in play, interpreter's encoding; 2 = kernels in play, jit forms
+    const bool jit_forms = forms >= 2, stable_slot = forms >= 1;
     constexpr int M = Cfg::M, LOW = Cfg::LOW, R = Cfg::R, NTB = M - R, SB = Swz<T2>::B;
     constexpr bool is_double = sizeof(T2) == 16;
     constexpr size_t kMinLadder = 6; // shorter runs are cheaper as ordinary ops in the lean kernel
@@ -973,7 +976,7 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
             if (r + 1 == hq.rounds.size()) {
                 const double mag = std::abs(sigma);
                 const bool fold = sigma != cd(1.0) && (Cfg::NS == 2 || tape_done || mag < sig_lo || mag > sig_hi);
-                top[op_cursor++] = scale_op(fold ? sigma : cd(1.0));
+                if (fold || stable_slot) top[op_cursor++] = scale_op(fold ? sigma : cd(1.0));
                 if (fold) sigma = cd(1.0);
             }
             rh[r].nops = op_cursor - rh[r].first_op;
@@ -1166,7 +1169,7 @@ template <typename T2> void run_fused_typed(StateVec &sv, const std::vector<COp>
         PLB_CUDA(cudaEventCreate(&ev0));
         PLB_CUDA(cudaEventCreate(&ev1));
     }
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit ? (jit_forms_enabled() ? 2 : 1) : 0,
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (trace) PLB_CUDA(cudaEventRecord(ev0, sv.stream));
         if (st.op >= 0) launch_op(sv, items[st.op].op);
@@ -1225,7 +1228,7 @@ template <typename T2> bool run_fused_routed_typed(StateVec &sv, const std::vect
         else launch_pass<T2, Cfg>(st, sv.stream, static_cast<T2 *>(sv.data), nullptr, nullptr, pp);
         sv.launches++;
     };
-    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+    build_schedule<T2, Cfg>(static_cast<int>(sv.n), sv.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled() ? 2 : 1,
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (have) launch_plain(held_st, *held), have = false; // the held pass was not the last step
         if (st.op >= 0) launch_op(sv, items[st.op].op);
@@ -1280,7 +1283,7 @@ void run_adjoint_typed(StateVec &lambda, StateVec &hl, const std::vector<AdjItem
         std::vector<double> scale;
     };
     std::vector<PassSlots> passes;
-    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), use_jit && jit_forms_enabled(),
+    build_schedule<T2, Cfg>(static_cast<int>(lambda.n), lambda.sm_count, items, scaled_forms_enabled(), use_jit ? (jit_forms_enabled() ? 2 : 1) : 0,
                             [&](const Step &st, const PassParams<T2> *pp) -> bool {
         if (st.op >= 0) {
             const AdjItem &it = items[st.op];
@@ -1425,8 +1428,8 @@ void schedule_stats(int n, int precision, const std::vector<COp> &ops, int64_t o
         if (s.op >= 0) out[1]++;
         else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
     };
-    if (precision == 64) build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, false, count);
-    else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, false, count);
+    if (precision == 64) build_schedule<double2, FwdCfg<double2>>(n, 148, items, true, 0, count);
+    else build_schedule<float2, FwdCfg<float2>>(n, 148, items, true, 0, count);
 }
 
 // Host-only: the specialised source of every tile pass of the tape (tools, tests, compile-time checks).
@@ -1442,7 +1445,7 @@ void pass_sources(int n, int precision, const std::vector<COp> &ops, std::vector
     auto run = [&](auto t2, auto cfg) {
         using T2 = decltype(t2);
         using Cfg = decltype(cfg);
-        build_schedule<T2, Cfg>(n, 148, items, true, jit_forms, [&](const Step &s, const PassParams<T2> *pp) -> bool {
+        build_schedule<T2, Cfg>(n, 148, items, true, jit_forms ? 2 : 1, [&](const Step &s, const PassParams<T2> *pp) -> bool {
             if (s.op != -1) return true;
             if (jit_forms && !s.jit_forms && refuse && !out.empty() && out.back() == "\x01") { // the interpreter encoding of a refused pass
                 out.pop_back();
@@ -1535,7 +1538,7 @@ int emulate_typed(int n, const std::vector<AdjItem> &items, bool scaled, T2 *sv0
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
     int rc = 0;
     const char *jfe = std::getenv("PLB200_JIT_FORMS");
-    const bool jit_forms = std::getenv("PLB200_EMU_JIT") != nullptr && !(jfe && jfe[0] == '0');
+    const int jit_forms = std::getenv("PLB200_EMU_JIT") == nullptr ? 0 : (jfe && jfe[0] == '0') ? 1 : 2;
     // PLB200_EMU_REFUSE=1: refuse every pass that needs a specialised kernel, as a consumer without that kernel does
     const bool refuse = std::getenv("PLB200_EMU_REFUSE") != nullptr;
     build_schedule<T2, Cfg>(n, 148, items, scaled, jit_forms, [&](const Step &st, const PassParams<T2> *pp) -> bool {
@@ -1585,7 +1588,7 @@ int emulate_routed_typed(int n, const std::vector<AdjItem> &items, bool scaled, 
         else emulate_pass<T2, Cfg, false>(sv0, nullptr, acc.data(), pp);
     };
     const char *jfe = std::getenv("PLB200_JIT_FORMS");
-    build_schedule<T2, Cfg>(n, 148, items, scaled, !(jfe && jfe[0] == '0'), [&](const Step &st, const PassParams<T2> *pp) {
+    build_schedule<T2, Cfg>(n, 148, items, scaled, (jfe && jfe[0] == '0') ? 1 : 2, [&](const Step &st, const PassParams<T2> *pp) {
         if (rc) return;
         if (have) plain(held_st, *held), have = false;
         if (st.op >= 0) rc = standalone(ctx, st.op);
@@ -1620,8 +1623,8 @@ void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem>
         if (s.op >= 0) out[1]++;
         else if (s.op == -1) out[0]++, out[2] += s.nrounds, out[3] += s.nops;
     };
-    if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, false, count);
-    else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, false, count);
+    if (precision == 64) build_schedule<double2, AdjCfg<double2>>(n, 148, items, true, 0, count);
+    else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, 0, count);
 }
 int64_t emu_jit_passes() { return g_emu_jit_passes; }
 void emu_kind_hist(int64_t out[32], bool reset) {
