@@ -20,6 +20,7 @@ int emulate_routed(int n, int precision, const std::vector<AdjItem> &items, bool
                    int (*standalone)(void *, int), void *ctx);
 void emu_kind_hist(int64_t out[32], bool reset);
 int64_t emu_jit_passes();
+int64_t emu_plan_hits();
 void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem> &items, int64_t out[4]);
 }
 using namespace plb200;
@@ -165,6 +166,8 @@ extern "C" {
 const char *plb200_emu_last_error(void) { return g_err.c_str(); }
 // passes executed through the g++-compiled specialised source (PLB200_EMU_JIT=1) so far
 int64_t plb200_emu_jit_passes(void) { return emu_jit_passes(); }
+// tapes whose schedule came from the plan cache so far
+int64_t plb200_emu_plan_hits(void) { return emu_plan_hits(); }
 // ops emitted by the pass encoder per interpreter kind (tile_exec.cuh enum) since the last reset
 void plb200_emu_kind_histogram(int64_t *out32, int reset) { emu_kind_hist(out32, reset != 0); }
 

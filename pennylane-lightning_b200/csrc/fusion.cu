@@ -24,7 +24,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 
 #include "jit_codegen.hpp"
 #include "jit_runtime.hpp"
@@ -362,6 +364,7 @@ uint64_t grow(const std::vector<FOp> &f, const std::vector<int> &pending, uint64
 
 #if defined(PLB200_HOST_EMU)
 int64_t g_kind_hist[32] = {0}; // encoder coverage: ops emitted per kind (test-only)
+int64_t g_plan_hits = 0;       // tapes scheduled from a cached plan (test-only)
 #endif
 
 struct HostPass {
@@ -516,90 +519,72 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
         return t;
     };
 
-    while (true) {
-        while (first < items.size() && done[first]) first++;
-        if (first >= items.size()) break;
-        pending.clear();
-        for (size_t i = first; i < items.size() && pending.size() < window; i++)
-            if (!done[i]) pending.push_back(static_cast<int>(i));
-        // ---- choose the tile bits
-        uint64_t T = grow(f, pending, lowbits, M, full, full, exec);
-        if (multistart) {
-            // greedy growth restarted from every bit some pending op needs: keeps the best tile.
-            // (30q benchmark tape: 24 -> 20 passes for ~2 ms more host time per pass, hidden behind
-            // the previous pass running on the GPU; not worth it for states a pass sweeps in microseconds)
-            uint64_t cand = 0;
-            for (int i : pending) cand |= f[i].nd;
-            cand &= full & ~lowbits;
-            std::vector<int> ex2;
-            for (int b = 0; b < n; b++) {
-                if (!(cand >> b & 1)) continue;
-                const uint64_t Tc = grow(f, pending, lowbits | (uint64_t{1} << b), M, full, full, ex2);
-                if (ex2.size() > exec.size()) exec = ex2, T = Tc;
-            }
+    // records an item may emit (caps the ops of a pass; a pivoted 2x2 block emits two, a dense 4x4 four, ...)
+    std::vector<uint8_t> wt(items.size(), 1);
+    for (size_t i = 0; i < items.size(); i++) {
+        const AdjItem &it = items[i];
+        size_t w = 1;
+        if (!it.overlap && it.op.kind == OP_DENSE) w = 4; // K_DENSE2: one record per matrix row
+        else if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op))
+            w = 2 * it.op.blocks.size(); // K_PAIR2 / K_PAIR4: one record per block (+ a pivot each at most)
+        else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG && it.op.cmask != 0 && __builtin_popcountll(f[i].pmask) == 1 &&
+                 f[i].d[0] != cd(1.0))
+            w = 2; // a controlled two-valued diagonal may split into two controlled phases
+        else if (!it.overlap && it.op.kind == OP_PAIRS && f[i].fusable && !it.op.blocks.empty()) {
+            // a 2x2 block may need a pivot (an X first): two records — except the forms that never do, whatever
+            // their angle: X itself, and the uncontrolled rotations / Hadamard whose scalar goes to the host.  The
+            // weight must not depend on the angle (it is part of the plan's signature).
+            const cd *m = it.op.blocks[0].m;
+            const bool is_x = m[0] == cd(0.0) && m[3] == cd(0.0) && m[1] == cd(1.0) && m[2] == cd(1.0);
+            const bool all_real = is_real(m[0]) && is_real(m[1]) && is_real(m[2]) && is_real(m[3]);
+            const bool rx_like = is_real(m[0]) && is_real(m[3]) && is_imag(m[1]) && is_imag(m[2]);
+            const bool ry = all_real && m[0] == m[3] && m[1] == -m[2];
+            const bool rx = rx_like && m[0] == m[3] && m[1] == m[2];
+            const double c = m[0].real(), sn = ry ? m[2].real() : -m[2].imag();
+            const bool rot = (ry || rx) && std::abs(c * c + sn * sn - 1.0) <= 8e-16;
+            const bool had = all_real && m[0] == m[1] && m[0] == m[2] && m[0] == -m[3] && m[0] != cd(0.0);
+            w = (is_x || (allow_scaled && it.op.cmask == 0 && (rot || had))) ? 1 : 2;
         }
-        if (exec.size() < 2) {
-            // nothing worth a tile pass: run the first pending item on its own
-            Step st;
-            st.op = static_cast<int>(first);
-            on_step(st, nullptr);
-            done[first] = 1;
-            continue;
-        }
-        // pad T to exactly M bits with the lowest free bits
-        for (int b = 0; b < n && __builtin_popcountll(T) < M; b++) T |= uint64_t{1} << b;
-        simulate(f, pending, T, full, exec);
-        {
-            // cap the EMITTED ops (a pivoted 2x2 block emits two); a prefix stays valid
-            size_t emitted = 0, keep = 0;
-            for (int i : exec) {
-                const AdjItem &it = items[i];
-                if (!it.overlap && it.op.kind == OP_DENSE)
-                    emitted += 4; // K_DENSE2: one record per matrix row
-                else if (!it.overlap && it.op.kind == OP_PAIRS && it.op.tbits.size() >= 2 && !is_swap2(it.op))
-                    emitted += 2 * it.op.blocks.size(); // K_PAIR2 / K_PAIR4: one record per block (+ a pivot each at most)
-                else if (jit_forms && !it.overlap && it.op.kind == OP_DIAG && it.op.cmask != 0 &&
-                         __builtin_popcountll(f[i].pmask) == 1 && f[i].d[0] != cd(1.0))
-                    emitted += 2; // a controlled two-valued diagonal may split into two controlled phases
-                else
-                    emitted += (!it.overlap && it.op.kind == OP_PAIRS && pair_form(it.op.blocks[0].m, false).pre_swap) ? 2 : 1;
-                if (emitted > max_pass_ops) break;
-                keep++;
-            }
-            exec.resize(keep);
-        }
-        std::vector<int> pass_ops = exec;
-
-        // ---- rounds
+        wt[i] = static_cast<uint8_t>(std::min<size_t>(w, 255));
+    }
+    // ---- plan cache.  The plan (which items form which pass, its tile bits, its rounds) is a function of the items'
+    // scheduling signature only — bit masks, fusability, record weights — not of their angles: a variational loop or
+    // an adjoint sweep per optimiser step re-encodes the cached plan with fresh values and skips the search.
+    struct PlanStep {
+        int op = -1;
         HostPass hp;
-        for (int b = 0; b < n; b++)
-            if (T >> b & 1) hp.tbits.push_back(b);
-        std::vector<int> rem = pass_ops, rexec;
-        while (!rem.empty()) {
-            uint64_t seed = f[rem[0]].nd; // guarantees progress
-            uint64_t Rb = grow(f, rem, seed, R, T, full, rexec);
-            // pad to R bits with tile bits (prefer high local bits)
-            for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < R; i--) Rb |= uint64_t{1} << hp.tbits[i];
-            simulate(f, rem, Rb, full, rexec);
-            if (rexec.empty()) fail("fusion scheduler made no progress");
-            hp.rounds.push_back(rexec);
-            hp.round_bits.push_back(Rb);
-            std::vector<int> next;
-            size_t k = 0;
-            for (int i : rem) {
-                if (k < rexec.size() && rexec[k] == i) k++;
-                else next.push_back(i);
-            }
-            rem.swap(next);
-            if (hp.rounds.size() == static_cast<size_t>(kMaxPassRounds)) break; // rest waits for the next pass
-        }
-        pass_ops.clear();
-        for (const auto &r : hp.rounds) pass_ops.insert(pass_ops.end(), r.begin(), r.end());
-        for (int i : pass_ops) done[i] = 1;
-        // the last step of the tape?  (then the carried scalar is multiplied back here)
-        bool tape_ends = true;
-        for (size_t i = first; i < items.size() && tape_ends; i++) tape_ends = done[i] != 0;
-
+        bool tape_ends = false;
+    };
+    struct Plan {
+        std::vector<uint64_t> sig;
+        std::vector<PlanStep> steps;
+    };
+    static std::mutex cache_mutex;
+    static std::deque<std::shared_ptr<const Plan>> cache;
+    const bool use_cache = !(std::getenv("PLB200_SCHED_CACHE") && std::getenv("PLB200_SCHED_CACHE")[0] == '0');
+    auto plan = std::make_shared<Plan>();
+    plan->sig = {static_cast<uint64_t>(n), static_cast<uint64_t>(M), static_cast<uint64_t>(R), static_cast<uint64_t>(Cfg::NS),
+                 static_cast<uint64_t>(sizeof(T2)), static_cast<uint64_t>(jit_forms), static_cast<uint64_t>(multistart),
+                 static_cast<uint64_t>(window), static_cast<uint64_t>(allow_scaled), static_cast<uint64_t>(items.size())};
+    for (size_t i = 0; i < items.size(); i++) {
+        plan->sig.push_back(f[i].nd);
+        plan->sig.push_back(f[i].all);
+        plan->sig.push_back(static_cast<uint64_t>(f[i].fusable) | static_cast<uint64_t>(wt[i]) << 1);
+    }
+    std::shared_ptr<const Plan> hit;
+    if (use_cache) {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        for (const auto &c : cache)
+            if (c->sig == plan->sig) hit = c;
+    }
+#if defined(PLB200_HOST_EMU)
+    if (hit) g_plan_hits++;
+#endif
+    // Encode one planned pass (tile bits + rounds) at the current carried scalar and hand it to the consumer; when the
+    // consumer refuses it, encode it again in the interpreter's forms / cut it at its pair ops.
+    auto run_pass = [&](const HostPass &hp, const bool tape_ends) {
+        uint64_t T = 0;
+        for (int b : hp.tbits) T |= uint64_t{1} << b;
         // ---- encode the plan (jf: in the forms of the specialised kernels)
         auto encode = [&](const bool jf, const HostPass &hq, const bool tape_done) -> Step {
         std::memset(static_cast<void *>(cur.get()), 0, sizeof(PassParams<T2>));
@@ -1045,6 +1030,101 @@ void build_schedule(int n, int sm_count, const std::vector<AdjItem> &items, bool
                 }
                 flush_piece(true); // (a scalar left when the pass ends with a pair op is folded by a later slot / the final sweep)
             }
+        }
+    };
+
+    if (hit) {
+        for (const PlanStep &ps : hit->steps) {
+            if (ps.op >= 0) {
+                Step st;
+                st.op = ps.op;
+                on_step(st, nullptr);
+            } else
+                run_pass(ps.hp, ps.tape_ends);
+        }
+    } else {
+    while (true) {
+        while (first < items.size() && done[first]) first++;
+        if (first >= items.size()) break;
+        pending.clear();
+        for (size_t i = first; i < items.size() && pending.size() < window; i++)
+            if (!done[i]) pending.push_back(static_cast<int>(i));
+        // ---- choose the tile bits
+        uint64_t T = grow(f, pending, lowbits, M, full, full, exec);
+        if (multistart) {
+            // greedy growth restarted from every bit some pending op needs: keeps the best tile.
+            // (30q benchmark tape: 24 -> 20 passes for ~2 ms more host time per pass, hidden behind
+            // the previous pass running on the GPU; not worth it for states a pass sweeps in microseconds)
+            uint64_t cand = 0;
+            for (int i : pending) cand |= f[i].nd;
+            cand &= full & ~lowbits;
+            std::vector<int> ex2;
+            for (int b = 0; b < n; b++) {
+                if (!(cand >> b & 1)) continue;
+                const uint64_t Tc = grow(f, pending, lowbits | (uint64_t{1} << b), M, full, full, ex2);
+                if (ex2.size() > exec.size()) exec = ex2, T = Tc;
+            }
+        }
+        if (exec.size() < 2) {
+            // nothing worth a tile pass: run the first pending item on its own
+            Step st;
+            st.op = static_cast<int>(first);
+            plan->steps.push_back(PlanStep{st.op, HostPass{}, false});
+            on_step(st, nullptr);
+            done[first] = 1;
+            continue;
+        }
+        // pad T to exactly M bits with the lowest free bits
+        for (int b = 0; b < n && __builtin_popcountll(T) < M; b++) T |= uint64_t{1} << b;
+        simulate(f, pending, T, full, exec);
+        {
+            // cap the EMITTED ops (a pivoted 2x2 block emits two); a prefix stays valid
+            size_t emitted = 0, keep = 0;
+            for (int i : exec) {
+                emitted += wt[i];
+                if (emitted > max_pass_ops) break;
+                keep++;
+            }
+            exec.resize(keep);
+        }
+        std::vector<int> pass_ops = exec;
+
+        // ---- rounds
+        HostPass hp;
+        for (int b = 0; b < n; b++)
+            if (T >> b & 1) hp.tbits.push_back(b);
+        std::vector<int> rem = pass_ops, rexec;
+        while (!rem.empty()) {
+            uint64_t seed = f[rem[0]].nd; // guarantees progress
+            uint64_t Rb = grow(f, rem, seed, R, T, full, rexec);
+            // pad to R bits with tile bits (prefer high local bits)
+            for (int i = M - 1; i >= 0 && __builtin_popcountll(Rb) < R; i--) Rb |= uint64_t{1} << hp.tbits[i];
+            simulate(f, rem, Rb, full, rexec);
+            if (rexec.empty()) fail("fusion scheduler made no progress");
+            hp.rounds.push_back(rexec);
+            hp.round_bits.push_back(Rb);
+            std::vector<int> next;
+            size_t k = 0;
+            for (int i : rem) {
+                if (k < rexec.size() && rexec[k] == i) k++;
+                else next.push_back(i);
+            }
+            rem.swap(next);
+            if (hp.rounds.size() == static_cast<size_t>(kMaxPassRounds)) break; // rest waits for the next pass
+        }
+        pass_ops.clear();
+        for (const auto &r : hp.rounds) pass_ops.insert(pass_ops.end(), r.begin(), r.end());
+        for (int i : pass_ops) done[i] = 1;
+        // the last step of the tape?  (then the carried scalar is multiplied back here)
+        bool tape_ends = true;
+        for (size_t i = first; i < items.size() && tape_ends; i++) tape_ends = done[i] != 0;
+        plan->steps.push_back(PlanStep{-1, hp, tape_ends});
+        run_pass(hp, tape_ends);
+    }
+        if (use_cache) {
+            std::lock_guard<std::mutex> lock(cache_mutex);
+            cache.push_back(plan);
+            if (cache.size() > 32) cache.pop_front();
         }
     }
     if (sigma != cd(1.0)) {
@@ -1627,6 +1707,7 @@ void emu_adjoint_schedule_stats(int n, int precision, const std::vector<AdjItem>
     else build_schedule<float2, AdjCfg<float2>>(n, 148, items, true, 0, count);
 }
 int64_t emu_jit_passes() { return g_emu_jit_passes; }
+int64_t emu_plan_hits() { return g_plan_hits; }
 void emu_kind_hist(int64_t out[32], bool reset) {
     for (int i = 0; i < 32; i++) {
         out[i] = g_kind_hist[i];
